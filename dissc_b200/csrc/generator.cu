@@ -1,0 +1,717 @@
+// C-ABI + host-side plan of the vocoder forward (include/dissc_b200.h).
+//
+// Launch plan of one forward (resblock "1", the shipped configs: 97 launches):
+//   conv_pre  [embedding gather fused]                      -> act   (lrelu 0.1 applied in epilogue)
+//   per stage i:
+//     convT(act)                                            -> x_up
+//     per resblock j, per dilation m:
+//       K3: lrelu -> dilated conv -> lrelu                  -> xt    (in = x_up | r)
+//       K4: conv(xt) + residual                             -> r     (m < last)
+//           ... last m: MRF accumulate folded in: j==0 -> xs, j>0 -> xs += , last j -> lrelu((xs+v)/n_rk) -> act
+//   conv_post + tanh                                        -> out
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv1d.cuh"
+#include "conv_post.cuh"
+#include "convt1d.cuh"
+
+namespace dissc {
+
+thread_local char g_err[512] = "";
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ------------------------------------------------------------------------
+// weight packing (host)
+// ------------------------------------------------------------------------
+// -> [co_tile][chunk][CI_CHUNK][k][CO_TILE], zero padded.  transposed: source is (Cin,Cout,k).
+static std::vector<float> pack_weights(const float* w, int Cin, int Cout, int k, int co_tile, int ci_chunk,
+                                       bool transposed) {
+  const int n_cot = (Cout + co_tile - 1) / co_tile;
+  const int n_chunk = (Cin + ci_chunk - 1) / ci_chunk;
+  std::vector<float> out((size_t)n_cot * n_chunk * ci_chunk * k * co_tile, 0.f);
+  for (int ct = 0; ct < n_cot; ++ct)
+    for (int ch = 0; ch < n_chunk; ++ch)
+      for (int cl = 0; cl < ci_chunk; ++cl) {
+        const int ci = ch * ci_chunk + cl;
+        if (ci >= Cin) continue;
+        for (int j = 0; j < k; ++j)
+          for (int c = 0; c < co_tile; ++c) {
+            const int co = ct * co_tile + c;
+            if (co >= Cout) continue;
+            const float v = transposed ? w[((size_t)ci * Cout + co) * k + j] : w[((size_t)co * Cin + ci) * k + j];
+            out[((((size_t)ct * n_chunk + ch) * ci_chunk + cl) * k + j) * co_tile + c] = v;
+          }
+      }
+  return out;
+}
+
+static int conv_co_tile(int Cout) { return Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16); }
+static int conv_ci_chunk(int co_tile) { return co_tile == 16 ? 4 : 8; }
+static int convt_co_tile(int Cout) { return Cout >= 32 ? 32 : 16; }
+
+// ------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------
+template <int CO_TILE, int KW, int DIL, int CI_CHUNK, bool EMB>
+static int launch_conv_inst(const ConvParams& p, cudaStream_t st) {
+  using C = ConvCfg<CO_TILE, KW, DIL, CI_CHUNK>;
+  auto kern = conv1d_fused_kernel<CO_TILE, KW, DIL, CI_CHUNK, EMB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DISSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((p.T + C::T_TILE - 1) / C::T_TILE, (p.Cout + CO_TILE - 1) / CO_TILE, p.B);
+  kern<<<grid, kThreads, C::SMEM, st>>>(p);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+template <int CO_TILE, int CI_CHUNK>
+static int launch_conv_cot(const ConvParams& p, int k, int dil, bool emb, cudaStream_t st) {
+#define DISSC_CONV_CASE(KW, DIL)                                                     \
+  if (k == KW && dil == DIL) {                                                       \
+    if (emb) {                                                                       \
+      if constexpr (KW == 7 && DIL == 1)                                             \
+        return launch_conv_inst<CO_TILE, KW, DIL, CI_CHUNK, true>(p, st);            \
+      else                                                                           \
+        return set_err(DISSC_EUNSUPPORTED, "embedding-fused conv only for k=7");     \
+    }                                                                                \
+    return launch_conv_inst<CO_TILE, KW, DIL, CI_CHUNK, false>(p, st);               \
+  }
+  DISSC_CONV_CASE(1, 1)
+  DISSC_CONV_CASE(3, 1) DISSC_CONV_CASE(3, 3) DISSC_CONV_CASE(3, 5)
+  DISSC_CONV_CASE(5, 1) DISSC_CONV_CASE(5, 3) DISSC_CONV_CASE(5, 5)
+  DISSC_CONV_CASE(7, 1) DISSC_CONV_CASE(7, 3) DISSC_CONV_CASE(7, 5)
+  DISSC_CONV_CASE(11, 1) DISSC_CONV_CASE(11, 3) DISSC_CONV_CASE(11, 5)
+#undef DISSC_CONV_CASE
+  return set_err(DISSC_EUNSUPPORTED, "conv1d kernel_size=%d dilation=%d has no sm_100a instantiation", k, dil);
+}
+
+static bool conv_supported(int k, int dil) {
+  if (k == 1) return dil == 1;
+  return (k == 3 || k == 5 || k == 7 || k == 11) && (dil == 1 || dil == 3 || dil == 5);
+}
+
+static int launch_conv(const ConvParams& p, int k, int dil, int co_tile, bool emb, cudaStream_t st) {
+  switch (co_tile) {
+    case 64: return launch_conv_cot<64, 8>(p, k, dil, emb, st);
+    case 32: return launch_conv_cot<32, 8>(p, k, dil, emb, st);
+    case 16: return launch_conv_cot<16, 4>(p, k, dil, emb, st);
+  }
+  return set_err(DISSC_EINVAL, "bad co_tile %d", co_tile);
+}
+
+template <int CO_TILE, int KW, int U>
+static int launch_convt_inst(const ConvTParams& p, cudaStream_t st) {
+  using C = ConvTCfg<CO_TILE, KW, U, 8>;
+  auto kern = convt1d_kernel<CO_TILE, KW, U, 8>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DISSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr_set = true;
+  }
+  const int n_frames = (p.Tout + p.pad - 1) / U + 1;
+  dim3 grid((n_frames + C::F_TILE - 1) / C::F_TILE, (p.Cout + CO_TILE - 1) / CO_TILE, p.B);
+  kern<<<grid, kThreads, C::SMEM, st>>>(p);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+static bool convt_supported(int k, int u) {
+  return (k == 11 && u == 5) || (k == 8 && u == 4) || (k == 4 && u == 2) || (k == 16 && u == 8);
+}
+
+static int launch_convt(const ConvTParams& p, int k, int u, int co_tile, cudaStream_t st) {
+#define DISSC_CONVT_CASE(KW, U)                                             \
+  if (k == KW && u == U) {                                                  \
+    if (co_tile == 32) return launch_convt_inst<32, KW, U>(p, st);          \
+    return launch_convt_inst<16, KW, U>(p, st);                             \
+  }
+  DISSC_CONVT_CASE(11, 5) DISSC_CONVT_CASE(8, 4) DISSC_CONVT_CASE(4, 2) DISSC_CONVT_CASE(16, 8)
+#undef DISSC_CONVT_CASE
+  return set_err(DISSC_EUNSUPPORTED, "conv_transpose1d kernel_size=%d stride=%d has no sm_100a instantiation", k, u);
+}
+
+static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
+  if (k != 7) return set_err(DISSC_EUNSUPPORTED, "conv_post kernel_size=%d (only 7)", k);
+  if (p.Cin > kPostMaxCin) return set_err(DISSC_EUNSUPPORTED, "conv_post Cin=%d > %d", p.Cin, kPostMaxCin);
+  dim3 grid((p.T + kPostTile - 1) / kPostTile, p.B);
+  conv_post_kernel<7><<<grid, kThreads, 0, st>>>(p);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+// ------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------
+struct ConvLayer {
+  int Cin = 0, Cout = 0, k = 0, dil = 1, pad = 0, co_tile = 0;
+  float* w = nullptr;  // packed, device
+  float* bias = nullptr;
+};
+struct ConvTLayer {
+  int Cin = 0, Cout = 0, k = 0, u = 0, pad = 0, co_tile = 0;
+  float* w = nullptr;
+  float* bias = nullptr;
+};
+
+struct Profiler {
+  char (*names)[64];
+  float* ms;
+  double* flops;
+  int cap;
+  int n = 0;
+  std::vector<cudaEvent_t> ev;
+};
+
+}  // namespace dissc
+
+using namespace dissc;
+
+struct dissc_gen {
+  dissc_gen_cfg cfg;
+  int device = 0;
+  int hop = 1;
+  std::vector<void*> allocs;
+  ConvLayer pre, post;
+  float* post_w_plain = nullptr;  // (Cin,k) for conv_post
+  ConvTLayer ups[DISSC_MAX_STAGES];
+  // rb[stage][j][m][0|1]  (ResBlock2 uses only [0])
+  ConvLayer rb[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS][2];
+  float* dict_w = nullptr;
+  float* spkr_w = nullptr;
+  int n_launches = 0;
+  // host-entry staging arena
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  cudaStream_t hstream = nullptr;
+};
+
+namespace dissc {
+
+static int dev_upload(dissc_gen* g, const float* host, size_t n, float** out) {
+  float* d = nullptr;
+  DISSC_CUDA(cudaMalloc(&d, std::max<size_t>(n, 4) * sizeof(float)));
+  g->allocs.push_back(d);
+  DISSC_CUDA(cudaMemcpy(d, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return DISSC_OK;
+}
+
+struct WeightMap {
+  std::map<std::string, const dissc_tensor*> m;
+  const dissc_tensor* get(const std::string& k) const {
+    auto it = m.find(k);
+    return it == m.end() ? nullptr : it->second;
+  }
+};
+
+static int make_conv(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int Cin, int Cout, int k, int dil,
+                     ConvLayer* L) {
+  const dissc_tensor* w = wm.get(prefix + ".weight");
+  const dissc_tensor* b = wm.get(prefix + ".bias");
+  DISSC_CHECK(w && b, DISSC_EMISSING, "missing tensor %s.{weight,bias}", prefix.c_str());
+  DISSC_CHECK(w->numel == (int64_t)Cin * Cout * k, DISSC_EINVAL, "%s.weight has %lld elements, expected %d*%d*%d",
+              prefix.c_str(), (long long)w->numel, Cout, Cin, k);
+  DISSC_CHECK(b->numel == Cout, DISSC_EINVAL, "%s.bias has %lld elements, expected %d", prefix.c_str(),
+              (long long)b->numel, Cout);
+  DISSC_CHECK(conv_supported(k, dil), DISSC_EUNSUPPORTED, "%s: conv1d kernel_size=%d dilation=%d unsupported",
+              prefix.c_str(), k, dil);
+  L->Cin = Cin; L->Cout = Cout; L->k = k; L->dil = dil; L->pad = (k * dil - dil) / 2;
+  L->co_tile = conv_co_tile(Cout);
+  auto packed = pack_weights(w->data, Cin, Cout, k, L->co_tile, conv_ci_chunk(L->co_tile), false);
+  int rc = dev_upload(g, packed.data(), packed.size(), &L->w);
+  if (rc) return rc;
+  return dev_upload(g, b->data, Cout, &L->bias);
+}
+
+static int make_convt(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int Cin, int Cout, int k, int u,
+                      ConvTLayer* L) {
+  const dissc_tensor* w = wm.get(prefix + ".weight");
+  const dissc_tensor* b = wm.get(prefix + ".bias");
+  DISSC_CHECK(w && b, DISSC_EMISSING, "missing tensor %s.{weight,bias}", prefix.c_str());
+  DISSC_CHECK(w->numel == (int64_t)Cin * Cout * k && b->numel == Cout, DISSC_EINVAL, "%s: bad tensor sizes",
+              prefix.c_str());
+  DISSC_CHECK(convt_supported(k, u), DISSC_EUNSUPPORTED, "%s: conv_transpose1d kernel_size=%d stride=%d unsupported",
+              prefix.c_str(), k, u);
+  L->Cin = Cin; L->Cout = Cout; L->k = k; L->u = u; L->pad = (k - u) / 2;
+  L->co_tile = convt_co_tile(Cout);
+  auto packed = pack_weights(w->data, Cin, Cout, k, L->co_tile, 8, true);
+  int rc = dev_upload(g, packed.data(), packed.size(), &L->w);
+  if (rc) return rc;
+  return dev_upload(g, b->data, Cout, &L->bias);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// elements of the largest activation a (B,T) forward materialises
+static size_t max_act_elems(const dissc_gen* g, int B, int T) {
+  size_t mx = (size_t)B * g->cfg.c0 * T;
+  size_t t = T;
+  int ch = g->cfg.c0;
+  for (int i = 0; i < g->cfg.n_up; ++i) {
+    const ConvTLayer& U = g->ups[i];
+    t = (t - 1) * U.u - 2 * U.pad + U.k;
+    ch = U.Cout;
+    mx = std::max(mx, (size_t)B * ch * t);
+  }
+  return mx;
+}
+
+static int out_len(const dissc_gen* g, int T) {
+  long t = T;
+  for (int i = 0; i < g->cfg.n_up; ++i) t = (t - 1) * g->ups[i].u - 2 * g->ups[i].pad + g->ups[i].k;
+  return (int)t;
+}
+
+struct Launcher {
+  cudaStream_t st;
+  Profiler* prof;
+  int count = 0;
+  int begin(const char* name, double flops) {
+    ++count;
+    if (!prof) return DISSC_OK;
+    if (prof->n >= prof->cap) return set_err(DISSC_EINVAL, "profile capacity %d too small", prof->cap);
+    snprintf(prof->names[prof->n], 64, "%s", name);
+    prof->flops[prof->n] = flops;
+    cudaEvent_t e0, e1;
+    DISSC_CUDA(cudaEventCreate(&e0));
+    DISSC_CUDA(cudaEventCreate(&e1));
+    prof->ev.push_back(e0);
+    prof->ev.push_back(e1);
+    DISSC_CUDA(cudaEventRecord(e0, st));
+    return DISSC_OK;
+  }
+  int end() {
+    if (!prof) return DISSC_OK;
+    DISSC_CUDA(cudaEventRecord(prof->ev.back(), st));
+    prof->n++;
+    return DISSC_OK;
+  }
+};
+
+#define DISSC_TRY(expr)        \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != DISSC_OK) return _rc; \
+  } while (0)
+
+static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                        const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st, Profiler* prof) {
+  DISSC_CHECK(g && code && (out_f32 || out_i16), DISSC_EINVAL, "null handle / code / out");
+  DISSC_CHECK(B > 0 && T > 0, DISSC_EINVAL, "B=%d T=%d must be positive", B, T);
+  DISSC_CHECK(!g->cfg.has_f0 || f0, DISSC_EINVAL, "config has f0 but f0 == NULL");
+  DISSC_CHECK(!g->cfg.has_spkr || spkr, DISSC_EINVAL, "config is multi-speaker but spkr == NULL");
+  DISSC_CHECK(B <= 65535, DISSC_EINVAL, "B=%d exceeds gridDim.z limit 65535", B);
+  size_t need = 0;
+  dissc_gen_workspace_bytes(g, B, T, &need);
+  DISSC_CHECK(workspace && workspace_bytes >= need, DISSC_EINVAL, "workspace %zu bytes < required %zu", workspace_bytes,
+              need);
+  int dev = -1;
+  DISSC_CUDA(cudaGetDevice(&dev));
+  DISSC_CHECK(dev == g->device, DISSC_EINVAL, "current device %d != handle device %d", dev, g->device);
+
+  const size_t smax = align_up(max_act_elems(g, B, T) * sizeof(float), 256);
+  char* wsb = static_cast<char*>(workspace);
+  float* act[2] = {reinterpret_cast<float*>(wsb), reinterpret_cast<float*>(wsb + smax)};
+  float* x_up = reinterpret_cast<float*>(wsb + 2 * smax);
+  float* xt = reinterpret_cast<float*>(wsb + 3 * smax);
+  float* r = reinterpret_cast<float*>(wsb + 4 * smax);
+
+  Launcher L{st, prof};
+  const dissc_gen_cfg& c = g->cfg;
+  char name[64];
+
+  // conv_pre with fused gather/concat; epilogue applies the first stage's leaky-relu (sr/models.py:99,:101)
+  {
+    ConvParams p{};
+    p.code = reinterpret_cast<const long long*>(code);
+    p.f0 = f0;
+    p.spkr = reinterpret_cast<const long long*>(spkr);
+    p.dict_w = g->dict_w;
+    p.spkr_w = g->spkr_w;
+    p.E = c.embedding_dim;
+    p.f0_ch = c.has_f0 ? c.embedding_dim : -1;
+    p.spk_base = c.has_spkr ? c.embedding_dim + (c.has_f0 ? 1 : 0) : -1;
+    p.w = g->pre.w; p.bias = g->pre.bias; p.out = act[0];
+    p.lengths = lengths; p.len_mul = 1;
+    p.B = B; p.Cin = g->pre.Cin; p.Cout = g->pre.Cout; p.T = T; p.pad = g->pre.pad;
+    p.post_act = 1; p.post_slope = 0.1f;
+    if (c.n_up == 0) { p.post_slope = 0.01f; }
+    DISSC_TRY(L.begin("conv_pre", 2.0 * p.Cin * p.Cout * g->pre.k * (double)T * B));
+    DISSC_TRY(launch_conv(p, g->pre.k, 1, g->pre.co_tile, true, st));
+    DISSC_TRY(L.end());
+  }
+
+  int cur = 0;     // act[cur] holds the (already activated) stage input
+  int Tcur = T;    // time steps at the current rate
+  int mul = 1;     // valid length multiplier (product of rates so far)
+  for (int i = 0; i < c.n_up; ++i) {
+    const ConvTLayer& U = g->ups[i];
+    const int Tout = (Tcur - 1) * U.u - 2 * U.pad + U.k;
+    {
+      ConvTParams p{};
+      p.in = act[cur]; p.w = U.w; p.bias = U.bias; p.out = x_up;
+      p.lengths = lengths; p.len_mul = mul;
+      p.B = B; p.Cin = U.Cin; p.Cout = U.Cout; p.Tin = Tcur; p.Tout = Tout; p.pad = U.pad;
+      snprintf(name, sizeof(name), "ups.%d", i);
+      DISSC_TRY(L.begin(name, 2.0 * U.Cin * U.Cout * U.k * (double)Tcur * B));
+      DISSC_TRY(launch_convt(p, U.k, U.u, U.co_tile, st));
+      DISSC_TRY(L.end());
+    }
+    Tcur = Tout;
+    mul *= U.u;
+    const int ch = U.Cout;
+    float* xs = act[cur ^ 1];  // MRF accumulator; becomes the next stage's activated input
+    const bool last_stage = (i == c.n_up - 1);
+    const float next_slope = last_stage ? 0.01f : 0.1f;  // sr/models.py:110 vs :101
+    for (int j = 0; j < c.n_rk; ++j) {
+      for (int m = 0; m < c.n_dil; ++m) {
+        const bool last_m = (m == c.n_dil - 1);
+        const float* rin = (m == 0) ? x_up : r;
+        ConvParams p{};
+        p.lengths = lengths; p.len_mul = mul;
+        p.B = B; p.Cin = ch; p.Cout = ch; p.T = Tcur;
+        const ConvLayer& c1 = g->rb[i][j][m][0];
+        const double fl = 2.0 * ch * ch * (double)c1.k * Tcur * B;
+        if (c.resblock == 1) {
+          // K3: lrelu -> dilated conv -> lrelu     (sr/models.py:36-38)
+          p.in = rin; p.w = c1.w; p.bias = c1.bias; p.out = xt; p.pad = c1.pad;
+          p.pre_act = 1; p.pre_slope = 0.1f; p.post_act = 1; p.post_slope = 0.1f;
+          snprintf(name, sizeof(name), "s%d.rb%d.c1.%d", i, j, m);
+          DISSC_TRY(L.begin(name, fl));
+          DISSC_TRY(launch_conv(p, c1.k, c1.dil, c1.co_tile, false, st));
+          DISSC_TRY(L.end());
+        }
+        // K4: conv -> + residual [-> MRF accumulate]  (:39-40, :104-109)
+        const ConvLayer& c2 = (c.resblock == 1) ? g->rb[i][j][m][1] : c1;
+        ConvParams q{};
+        q.lengths = lengths; q.len_mul = mul;
+        q.B = B; q.Cin = ch; q.Cout = ch; q.T = Tcur;
+        q.w = c2.w; q.bias = c2.bias; q.pad = c2.pad; q.res = rin;
+        if (c.resblock == 1) {
+          q.in = xt;
+        } else {
+          q.in = rin; q.pre_act = 1; q.pre_slope = 0.1f;  // ResBlock2: lrelu -> conv -> +x (:63-66)
+        }
+        if (!last_m) {
+          q.out = r;
+        } else {
+          q.out = xs;
+          if (j > 0) q.acc_in = xs;
+          if (j == c.n_rk - 1) {
+            q.div = (float)c.n_rk;
+            q.post_act = 1; q.post_slope = next_slope;
+          }
+        }
+        snprintf(name, sizeof(name), "s%d.rb%d.c2.%d", i, j, m);
+        DISSC_TRY(L.begin(name, fl));
+        DISSC_TRY(launch_conv(q, c2.k, c2.dil, c2.co_tile, false, st));
+        DISSC_TRY(L.end());
+      }
+    }
+    cur ^= 1;
+  }
+
+  {
+    ConvPostParams p{};
+    p.in = act[cur]; p.w = g->post_w_plain; p.bias = g->post.bias;
+    p.out_f32 = out_f32; p.out_i16 = out_i16;
+    p.lengths = lengths; p.len_mul = mul;
+    p.B = B; p.Cin = g->post.Cin; p.T = Tcur;
+    DISSC_TRY(L.begin("conv_post", 2.0 * p.Cin * g->post.k * (double)Tcur * B));
+    DISSC_TRY(launch_conv_post(p, g->post.k, st));
+    DISSC_TRY(L.end());
+  }
+  g->n_launches = L.count;
+  return DISSC_OK;
+}
+
+}  // namespace dissc
+
+// ------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------
+extern "C" {
+
+const char* dissc_last_error(void) { return dissc::g_err; }
+const char* dissc_version(void) { return "dissc_b200 0.1 (sm_100a)"; }
+
+int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_tensor* weights, int n_weights,
+                     int device) {
+  DISSC_CHECK(out && cfg && weights, DISSC_EINVAL, "null argument");
+  *out = nullptr;
+  const dissc_gen_cfg& c = *cfg;
+  DISSC_CHECK(c.n_up >= 0 && c.n_up <= DISSC_MAX_STAGES && c.n_rk > 0 && c.n_rk <= DISSC_MAX_KERNELS && c.n_dil > 0 &&
+                  c.n_dil <= DISSC_MAX_DILATIONS,
+              DISSC_EINVAL, "bad stage/kernel counts");
+  DISSC_CHECK(c.resblock == 1 || c.resblock == 2, DISSC_EUNSUPPORTED, "resblock must be \"1\" or \"2\"");
+  const int expect_in = c.embedding_dim + (c.has_f0 ? 1 : 0) + (c.has_spkr ? c.embedding_dim : 0);
+  DISSC_CHECK(c.model_in_dim == expect_in, DISSC_EUNSUPPORTED,
+              "model_in_dim=%d but embedding_dim/f0/multispkr give %d channels (extra conditioning features such as "
+              "f0_stats are not supported)",
+              c.model_in_dim, expect_in);
+  DISSC_CUDA(cudaSetDevice(device));
+  WeightMap wm;
+  for (int i = 0; i < n_weights; ++i) wm.m[weights[i].name] = &weights[i];
+
+  dissc_gen* g = new dissc_gen();
+  g->cfg = c;
+  g->device = device;
+  auto fail = [&](int rc) {
+    dissc_gen_destroy(g);
+    return rc;
+  };
+  int rc;
+  if ((rc = make_conv(g, wm, "conv_pre", c.model_in_dim, c.c0, 7, 1, &g->pre))) return fail(rc);
+  int ch = c.c0;
+  g->hop = 1;
+  for (int i = 0; i < c.n_up; ++i) {
+    const int ci = c.c0 >> i, co = c.c0 >> (i + 1);
+    if (co < 1) return fail(set_err(DISSC_EINVAL, "upsample_initial_channel too small for %d stages", c.n_up));
+    if ((rc = make_convt(g, wm, "ups." + std::to_string(i), ci, co, c.up_kernels[i], c.up_rates[i], &g->ups[i])))
+      return fail(rc);
+    ch = co;
+    g->hop *= c.up_rates[i];
+    for (int j = 0; j < c.n_rk; ++j)
+      for (int m = 0; m < c.n_dil; ++m) {
+        const std::string p = "resblocks." + std::to_string(i * c.n_rk + j);
+        if (c.resblock == 1) {
+          if ((rc = make_conv(g, wm, p + ".convs1." + std::to_string(m), ch, ch, c.rk[j], c.dil[j][m],
+                              &g->rb[i][j][m][0])))
+            return fail(rc);
+          if ((rc = make_conv(g, wm, p + ".convs2." + std::to_string(m), ch, ch, c.rk[j], 1, &g->rb[i][j][m][1])))
+            return fail(rc);
+        } else {
+          if ((rc = make_conv(g, wm, p + ".convs." + std::to_string(m), ch, ch, c.rk[j], c.dil[j][m],
+                              &g->rb[i][j][m][0])))
+            return fail(rc);
+        }
+      }
+  }
+  // conv_post: (1, ch, 7) -> plain (ch, 7)
+  {
+    const dissc_tensor* w = wm.get("conv_post.weight");
+    const dissc_tensor* b = wm.get("conv_post.bias");
+    if (!w || !b) return fail(set_err(DISSC_EMISSING, "missing tensor conv_post.{weight,bias}"));
+    if (w->numel != (int64_t)ch * 7 || b->numel != 1) return fail(set_err(DISSC_EINVAL, "conv_post: bad tensor sizes"));
+    g->post.Cin = ch; g->post.Cout = 1; g->post.k = 7; g->post.pad = 3;
+    if ((rc = dev_upload(g, w->data, (size_t)ch * 7, &g->post_w_plain))) return fail(rc);
+    if ((rc = dev_upload(g, b->data, 1, &g->post.bias))) return fail(rc);
+  }
+  {
+    const dissc_tensor* d = wm.get("dict.weight");
+    if (!d || d->numel != (int64_t)c.num_embeddings * c.embedding_dim)
+      return fail(set_err(DISSC_EMISSING, "dict.weight missing or not (%d,%d)", c.num_embeddings, c.embedding_dim));
+    if ((rc = dev_upload(g, d->data, d->numel, &g->dict_w))) return fail(rc);
+    if (c.has_spkr) {
+      const dissc_tensor* s = wm.get("spkr.weight");
+      if (!s || s->numel != (int64_t)c.n_spkr_rows * c.embedding_dim)
+        return fail(set_err(DISSC_EMISSING, "spkr.weight missing or not (%d,%d)", c.n_spkr_rows, c.embedding_dim));
+      if ((rc = dev_upload(g, s->data, s->numel, &g->spkr_w))) return fail(rc);
+    }
+  }
+  g->n_launches = 1 + c.n_up * (1 + c.n_rk * c.n_dil * (c.resblock == 1 ? 2 : 1)) + 1;
+  *out = g;
+  return DISSC_OK;
+}
+
+void dissc_gen_destroy(dissc_gen_t* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  for (void* p : g->allocs) cudaFree(p);
+  if (g->arena) cudaFree(g->arena);
+  if (g->hstream) cudaStreamDestroy(g->hstream);
+  delete g;
+}
+
+int dissc_gen_hop(const dissc_gen_t* g) { return g ? g->hop : 0; }
+int dissc_gen_launches_per_forward(const dissc_gen_t* g) { return g ? g->n_launches : 0; }
+
+int dissc_gen_workspace_bytes(const dissc_gen_t* g, int B, int T, size_t* bytes) {
+  DISSC_CHECK(g && bytes && B > 0 && T > 0, DISSC_EINVAL, "bad argument");
+  *bytes = 5 * align_up(max_act_elems(g, B, T) * sizeof(float), 256);
+  return DISSC_OK;
+}
+
+int dissc_gen_forward(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                      const int32_t* lengths, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  return forward_impl(g, code, f0, spkr, lengths, B, T, out, nullptr, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int dissc_gen_forward_i16(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                          const int32_t* lengths, int B, int T, int16_t* out_i16, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return forward_impl(g, code, f0, spkr, lengths, B, T, nullptr, out_i16, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                           const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16) {
+  DISSC_CHECK(g && code && ((out_f32 != nullptr) != (out_i16 != nullptr)), DISSC_EINVAL,
+              "need a handle, code and exactly one output buffer");
+  DISSC_CHECK(B > 0 && T > 0, DISSC_EINVAL, "B=%d T=%d must be positive", B, T);
+  DISSC_CUDA(cudaSetDevice(g->device));
+  if (!g->hstream) DISSC_CUDA(cudaStreamCreateWithFlags(&g->hstream, cudaStreamNonBlocking));
+  size_t ws = 0;
+  dissc_gen_workspace_bytes(g, B, T, &ws);
+  const size_t n_out = (size_t)B * out_len(g, T);
+  const size_t b_code = align_up((size_t)B * T * 8, 256), b_f0 = align_up((size_t)B * T * 4, 256),
+               b_spk = align_up((size_t)B * 8, 256), b_len = align_up((size_t)B * 4, 256),
+               b_out = align_up(n_out * (out_f32 ? 4 : 2), 256);
+  const size_t total = b_code + b_f0 + b_spk + b_len + b_out + ws;
+  if (total > g->arena_bytes) {
+    if (g->arena) DISSC_CUDA(cudaFree(g->arena));
+    g->arena = nullptr;
+    g->arena_bytes = 0;
+    DISSC_CUDA(cudaMalloc(&g->arena, total));
+    g->arena_bytes = total;
+  }
+  char* a = static_cast<char*>(g->arena);
+  int64_t* d_code = reinterpret_cast<int64_t*>(a);
+  float* d_f0 = reinterpret_cast<float*>(a + b_code);
+  int64_t* d_spk = reinterpret_cast<int64_t*>(a + b_code + b_f0);
+  int32_t* d_len = reinterpret_cast<int32_t*>(a + b_code + b_f0 + b_spk);
+  char* d_out = a + b_code + b_f0 + b_spk + b_len;
+  void* d_ws = d_out + b_out;
+  cudaStream_t st = g->hstream;
+  DISSC_CUDA(cudaMemcpyAsync(d_code, code, (size_t)B * T * 8, cudaMemcpyHostToDevice, st));
+  if (f0) DISSC_CUDA(cudaMemcpyAsync(d_f0, f0, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
+  if (spkr) DISSC_CUDA(cudaMemcpyAsync(d_spk, spkr, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  if (lengths) DISSC_CUDA(cudaMemcpyAsync(d_len, lengths, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  int rc = forward_impl(g, d_code, f0 ? d_f0 : nullptr, spkr ? d_spk : nullptr, lengths ? d_len : nullptr, B, T,
+                        out_f32 ? reinterpret_cast<float*>(d_out) : nullptr,
+                        out_i16 ? reinterpret_cast<int16_t*>(d_out) : nullptr, d_ws, ws, st, nullptr);
+  if (rc) return rc;
+  if (out_f32)
+    DISSC_CUDA(cudaMemcpyAsync(out_f32, d_out, n_out * 4, cudaMemcpyDeviceToHost, st));
+  else
+    DISSC_CUDA(cudaMemcpyAsync(out_i16, d_out, n_out * 2, cudaMemcpyDeviceToHost, st));
+  DISSC_CUDA(cudaStreamSynchronize(st));
+  return DISSC_OK;
+}
+
+int dissc_gen_cost(const dissc_gen_t* g, int B, int T, double* flops, double* bytes) {
+  DISSC_CHECK(g && B > 0 && T > 0, DISSC_EINVAL, "bad argument");
+  const dissc_gen_cfg& c = g->cfg;
+  double fl = 2.0 * g->pre.Cin * g->pre.Cout * g->pre.k * T;
+  // layer-fused traffic model: every fused kernel reads each input once, writes its output once.
+  double by = (8.0 + (c.has_f0 ? 4.0 : 0.0)) * T + (c.has_spkr ? 8.0 : 0.0) + 4.0 * g->pre.Cout * T;
+  double wbytes = 4.0 * g->pre.Cin * g->pre.Cout * g->pre.k;
+  double t = T;
+  double s_prev = 4.0 * g->pre.Cout * T;
+  for (int i = 0; i < c.n_up; ++i) {
+    const ConvTLayer& U = g->ups[i];
+    fl += 2.0 * U.Cin * U.Cout * U.k * t;
+    wbytes += 4.0 * U.Cin * U.Cout * U.k;
+    t = (t - 1) * U.u - 2 * U.pad + U.k;
+    const double s = 4.0 * U.Cout * t;
+    by += s_prev + s;
+    const int per_pair = (c.resblock == 1) ? 5 : 3;  // K3: 1R+1W, K4: 2R+1W
+    by += s * (c.n_rk * c.n_dil * per_pair + (c.n_rk - 1));  // + the xs reads of the MRF accumulate
+    for (int j = 0; j < c.n_rk; ++j)
+      for (int m = 0; m < c.n_dil; ++m) {
+        const int nconv = (c.resblock == 1) ? 2 : 1;
+        fl += nconv * 2.0 * U.Cout * U.Cout * c.rk[j] * t;
+        wbytes += nconv * 4.0 * U.Cout * U.Cout * c.rk[j];
+      }
+    s_prev = s;
+  }
+  fl += 2.0 * g->post.Cin * g->post.k * t;
+  by += s_prev + 4.0 * t;
+  if (flops) *flops = fl * B;
+  if (bytes) *bytes = by * B + wbytes;
+  return DISSC_OK;
+}
+
+int dissc_gen_profile(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                      const int32_t* lengths, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                      char (*names)[64], float* ms, double* flops, int cap, int* n) {
+  DISSC_CHECK(names && ms && flops && n, DISSC_EINVAL, "null profile arrays");
+  Profiler prof{names, ms, flops, cap};
+  int rc = forward_impl(g, code, f0, spkr, lengths, B, T, out, nullptr, workspace, workspace_bytes, nullptr, &prof);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc == DISSC_OK && e == cudaSuccess)
+    for (int i = 0; i < prof.n; ++i) cudaEventElapsedTime(&ms[i], prof.ev[2 * i], prof.ev[2 * i + 1]);
+  for (cudaEvent_t ev : prof.ev) cudaEventDestroy(ev);
+  *n = prof.n;
+  if (rc) return rc;
+  DISSC_CUDA(e);
+  return DISSC_OK;
+}
+
+// ---- layer-level test entry points -------------------------------------
+int dissc_conv1d_fused(const float* in, const float* w_host, const float* bias_host, const float* res,
+                       const float* acc_in, float* out, const int32_t* lengths, int len_mul, int B, int Cin, int Cout,
+                       int T, int k, int dilation, int pre_act, float pre_slope, int post_act, float post_slope,
+                       float div, void* stream) {
+  DISSC_CHECK(in && w_host && out && B > 0 && Cin > 0 && Cout > 0 && T > 0, DISSC_EINVAL, "bad argument");
+  DISSC_CHECK(conv_supported(k, dilation), DISSC_EUNSUPPORTED, "conv1d kernel_size=%d dilation=%d unsupported", k,
+              dilation);
+  const int cot = conv_co_tile(Cout);
+  auto packed = pack_weights(w_host, Cin, Cout, k, cot, conv_ci_chunk(cot), false);
+  float *dw = nullptr, *db = nullptr;
+  DISSC_CUDA(cudaMalloc(&dw, packed.size() * 4));
+  cudaMemcpy(dw, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice);
+  if (bias_host) {
+    cudaMalloc(&db, Cout * 4);
+    cudaMemcpy(db, bias_host, Cout * 4, cudaMemcpyHostToDevice);
+  }
+  ConvParams p{};
+  p.in = in; p.w = dw; p.bias = db; p.res = res; p.acc_in = acc_in; p.out = out;
+  p.lengths = lengths; p.len_mul = len_mul;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.T = T; p.pad = (k * dilation - dilation) / 2;
+  p.pre_act = pre_act; p.pre_slope = pre_slope; p.post_act = post_act; p.post_slope = post_slope; p.div = div;
+  int rc = launch_conv(p, k, dilation, cot, false, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(dw);
+  if (db) cudaFree(db);
+  if (rc) return rc;
+  DISSC_CUDA(e);
+  return DISSC_OK;
+}
+
+int dissc_conv_transpose1d(const float* in, const float* w_host, const float* bias_host, float* out,
+                           const int32_t* lengths, int len_mul, int B, int Cin, int Cout, int T_in, int k, int u,
+                           void* stream) {
+  DISSC_CHECK(in && w_host && out && B > 0 && Cin > 0 && Cout > 0 && T_in > 0, DISSC_EINVAL, "bad argument");
+  DISSC_CHECK(convt_supported(k, u), DISSC_EUNSUPPORTED, "conv_transpose1d kernel_size=%d stride=%d unsupported", k, u);
+  const int cot = convt_co_tile(Cout);
+  auto packed = pack_weights(w_host, Cin, Cout, k, cot, 8, true);
+  float *dw = nullptr, *db = nullptr;
+  DISSC_CUDA(cudaMalloc(&dw, packed.size() * 4));
+  cudaMemcpy(dw, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice);
+  if (bias_host) {
+    cudaMalloc(&db, Cout * 4);
+    cudaMemcpy(db, bias_host, Cout * 4, cudaMemcpyHostToDevice);
+  }
+  ConvTParams p{};
+  p.in = in; p.w = dw; p.bias = db; p.out = out; p.lengths = lengths; p.len_mul = len_mul;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.Tin = T_in; p.pad = (k - u) / 2;
+  p.Tout = (T_in - 1) * u - 2 * p.pad + k;
+  int rc = launch_convt(p, k, u, cot, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(dw);
+  if (db) cudaFree(db);
+  if (rc) return rc;
+  DISSC_CUDA(e);
+  return DISSC_OK;
+}
+
+}  // extern "C"

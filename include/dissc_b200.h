@@ -1,0 +1,159 @@
+/*
+ * dissc_b200 -- C ABI of the B200-native DISSC inference hot path.
+ *
+ * The reference (gallilmaimon/DISSC) has no FFI of its own: its seam is the
+ * Python nn.Module surface used by its CLIs.  Each entry point below states
+ * the reference interface it replaces (file:line under the reference tree);
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 (DISSC_OK) or a negative DISSC_E* code; the
+ *     message for the calling thread's last failure is dissc_last_error().
+ *     Nothing throws, nothing calls exit().
+ *   - a handle is bound to one CUDA device and owns only its re-packed
+ *     weights (plus, for the *_host entry points, a cached staging arena).
+ *     Calls are asynchronous and ordered on the stream passed in (a
+ *     cudaStream_t passed as void*; NULL = the legacy default stream); no
+ *     internal host synchronisation unless the name ends in _host.
+ *   - a handle is not re-entrant across threads; distinct handles are
+ *     independent.  One process per GPU.
+ *   - activation layout is the reference's: (B, C, T) fp32, T contiguous.
+ */
+#ifndef DISSC_B200_H
+#define DISSC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DISSC_OK 0
+#define DISSC_EINVAL (-1)       /* bad argument / shape */
+#define DISSC_EUNSUPPORTED (-2) /* geometry the kernels do not implement */
+#define DISSC_ECUDA (-3)        /* CUDA runtime error (message has the cudaError string) */
+#define DISSC_ENOMEM (-4)
+#define DISSC_EMISSING (-5)     /* a required tensor is absent from the weight list */
+
+#define DISSC_MAX_STAGES 8
+#define DISSC_MAX_KERNELS 8
+#define DISSC_MAX_DILATIONS 8
+
+typedef struct {
+  const char* name; /* reference state-dict key, e.g. "resblocks.3.convs1.0.weight" */
+  const float* data; /* HOST pointer, fp32, contiguous, PyTorch layout */
+  int64_t numel;
+} dissc_tensor;
+
+/* ------------------------------------------------------------------ *
+ * Vocoder: CodeGenerator  (sr/models.py:72-225)
+ * ------------------------------------------------------------------ */
+
+/* Geometry = the keys of <ckpt_dir>/config.json that sr/models.py reads
+ * (Generator.__init__ :73-96, CodeGenerator.__init__ :126-156). */
+typedef struct {
+  int n_up;                                                 /* len(upsample_rates) */
+  int up_rates[DISSC_MAX_STAGES];                           /* upsample_rates */
+  int up_kernels[DISSC_MAX_STAGES];                         /* upsample_kernel_sizes */
+  int n_rk;                                                 /* len(resblock_kernel_sizes) */
+  int rk[DISSC_MAX_KERNELS];                                /* resblock_kernel_sizes */
+  int n_dil;                                                /* len(resblock_dilation_sizes[j]) */
+  int dil[DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];          /* resblock_dilation_sizes */
+  int c0;                                                   /* upsample_initial_channel */
+  int embedding_dim;                                        /* embedding_dim */
+  int num_embeddings;                                       /* num_embeddings (rows of dict.weight) */
+  int n_spkr_rows;                                          /* rows of spkr.weight (200, sr/models.py:133) */
+  int model_in_dim;                                         /* model_in_dim */
+  int resblock;                                             /* 1 = ResBlock1, 2 = ResBlock2 */
+  int has_f0;                                               /* h.f0 */
+  int has_spkr;                                             /* h.multispkr */
+} dissc_gen_cfg;
+
+typedef struct dissc_gen dissc_gen_t;
+
+/* Replaces: CodeGenerator(h).to(dev); load_state_dict(...); eval(); remove_weight_norm()
+ * (sr/inference.py:114-120,162-163).  `weights` are the FOLDED tensors
+ * (weight = g*v/||v||, sr/models.py:116-122) keyed by the reference names with
+ * suffix ".weight"/".bias", plus "dict.weight" and "spkr.weight".  They are
+ * copied and re-packed on the device; the caller may free them on return. */
+int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_tensor* weights, int n_weights,
+                     int device);
+void dissc_gen_destroy(dissc_gen_t* g);
+
+/* Total upsampling factor (prod(upsample_rates), 320 for the shipped configs). */
+int dissc_gen_hop(const dissc_gen_t* g);
+
+/* Bytes of device scratch dissc_gen_forward needs for a (B,T) batch. */
+int dissc_gen_workspace_bytes(const dissc_gen_t* g, int B, int T, size_t* bytes);
+
+/* Replaces: generator(code=..., f0=..., spkr=...)  (sr/inference.py:69 ->
+ * CodeGenerator.forward sr/models.py:179-225 -> Generator.forward :98-114).
+ * All pointers are DEVICE pointers on the handle's device.
+ *   code    int64 (B,T)      unit ids in [0,num_embeddings)
+ *   f0      fp32  (B,1,T)    may be NULL iff !has_f0
+ *   spkr    int64 (B,1)      may be NULL iff !has_spkr
+ *   lengths int32 (B)        valid frames per utterance, NULL = all T.  Frames
+ *                            >= lengths[b] behave exactly like the zero padding
+ *                            a B=1 reference call sees at the utterance's true
+ *                            end; out[b, t >= hop*lengths[b]] is written as 0.
+ *   out     fp32  (B,1,hop*T)
+ * Asynchronous on `stream`. */
+int dissc_gen_forward(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                      const int32_t* lengths, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Same, with the int16 conversion of generate() fused into the last kernel:
+ * audio = (y*32768).astype(int16)  (sr/inference.py:73-75; C-style truncation,
+ * +1.0 wraps to -32768 exactly like numpy).  out_i16 is (B, hop*T). */
+int dissc_gen_forward_i16(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                          const int32_t* lengths, int B, int T, int16_t* out_i16, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* End-to-end call with HOST buffers (what sr/inference.py:178 + :69 + :75 do per
+ * utterance, batched): H2D of the inputs, forward, D2H of the waveform, stream
+ * synchronise.  Pinned host memory makes the copies asynchronous; pageable
+ * memory works but serialises.  Exactly one of out_f32 / out_i16 is non-NULL. */
+int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                           const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16);
+
+/* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
+int dissc_gen_launches_per_forward(const dissc_gen_t* g);
+
+/* Algorithmic FLOPs and layer-fused-model bytes of one (B,T) forward. */
+int dissc_gen_cost(const dissc_gen_t* g, int B, int T, double* flops, double* bytes);
+
+/* Per-layer device timing of one forward (cudaEvent around every launch; debug /
+ * profiling aid).  names/ms are caller arrays of capacity `cap`; *n receives
+ * the number of launches.  Synchronises. */
+int dissc_gen_profile(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                      const int32_t* lengths, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                      char (*names)[64], float* ms, double* flops, int cap, int* n);
+
+/* ------------------------------------------------------------------ *
+ * Generic fused layers (exposed for layer-level parity tests)
+ * ------------------------------------------------------------------ */
+
+/* out = post( [acc_in +] [res +] bias + conv1d(pre(in), w) ) [/ div]
+ *   pre(x)  = leaky_relu(x, pre_slope)  if pre_act  else x
+ *   post(x) = leaky_relu(x, post_slope) if post_act else x
+ * w is (Cout,Cin,k) PyTorch layout on the HOST (packed internally per call --
+ * test entry point, not a fast path).  in/res/acc_in/out are DEVICE pointers. */
+int dissc_conv1d_fused(const float* in, const float* w_host, const float* bias_host, const float* res,
+                       const float* acc_in, float* out, const int32_t* lengths, int len_mul, int B, int Cin, int Cout,
+                       int T, int k, int dilation, int pre_act, float pre_slope, int post_act, float post_slope,
+                       float div, void* stream);
+
+/* out = bias + conv_transpose1d(in, w) with w (Cin,Cout,k) on the HOST, stride u, padding (k-u)/2. */
+int dissc_conv_transpose1d(const float* in, const float* w_host, const float* bias_host, float* out,
+                           const int32_t* lengths, int len_mul, int B, int Cin, int Cout, int T_in, int k, int u,
+                           void* stream);
+
+const char* dissc_last_error(void);
+const char* dissc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISSC_B200_H */

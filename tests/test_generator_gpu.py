@@ -1,0 +1,142 @@
+"""Vocoder parity on the GPU: dissc_b200.CodeGenerator (sm_100a kernels through the C ABI)
+vs the golden vectors of the real reference and vs the oracle on seeded inputs.
+
+Tolerance: north_star asks for <= 1e-4 max-abs on the waveform (values in [-1,1]);
+fp32 summation-order noise between the oracle's own thread counts is 1.6e-5."""
+import numpy as np
+import pytest
+import torch
+
+from _util import load_golden, make_generator, tiny_config, tiny_state_dict
+from dissc_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def vctk_gen(cuda_device):
+    sd = syn.synthetic_generator_state_dict(syn.VCTK_CONFIG, seed=0)
+    return make_generator(syn.VCTK_CONFIG, sd, cuda_device), sd
+
+
+def test_golden_tiny(cuda_device):
+    g = load_golden("gen_tiny.npz")
+    gen = make_generator(tiny_config(), tiny_state_dict(g), cuda_device)
+    y = gen(code=torch.from_numpy(g["code"]).to(cuda_device), f0=torch.from_numpy(g["f0"]).to(cuda_device),
+            spkr=torch.from_numpy(g["spkr"]).to(cuda_device))
+    assert tuple(y.shape) == g["y"].shape and y.is_cuda
+    err = np.abs(y.cpu().numpy() - g["y"]).max()
+    assert err < TOL, err
+
+
+def test_golden_vctk_T50(cuda_device, vctk_gen):
+    """BASELINE config 1 against the reference's own output."""
+    gen, sd = vctk_gen
+    g = load_golden("gen_vctk_T50.npz")
+    assert syn.state_dict_checksum(sd) == pytest.approx(float(g["sd_checksum"]), rel=1e-12)
+    y = gen(code=torch.from_numpy(g["code"]).to(cuda_device), f0=torch.from_numpy(g["f0"]).to(cuda_device),
+            spkr=torch.from_numpy(g["spkr"]).to(cuda_device))
+    err = np.abs(y.cpu().numpy() - g["y"]).max()
+    print("config-1 max-abs err vs reference:", err)
+    assert err < TOL, err
+
+
+def test_golden_ragged_batch(cuda_device, vctk_gen):
+    """H4: a padded batch with `lengths` equals per-utterance B=1 reference runs; tail is zero."""
+    gen, _ = vctk_gen
+    g = load_golden("gen_vctk_ragged.npz")
+    code = torch.from_numpy(g["code"]).to(cuda_device)
+    f0 = torch.from_numpy(g["f0"]).to(cuda_device).clone()
+    lengths = torch.from_numpy(g["lengths"]).to(cuda_device)
+    for b, n in enumerate(g["lengths"]):
+        f0[b, :, n:] = float("nan")  # padding content must not matter
+    y = gen(code=code, f0=f0, spkr=torch.from_numpy(g["spkr"]).to(cuda_device), lengths=lengths)
+    got = y.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - g["y"]).max()
+    assert err < TOL, err
+    for b, n in enumerate(g["lengths"]):
+        assert np.all(got[b, 0, 320 * n:] == 0)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 120)])
+def test_vs_oracle_seeded(cuda_device, vctk_gen, B, T):
+    from oracle import generator_oracle as go
+    gen, sd = vctk_gen
+    code, f0, spkr = syn.synthetic_inputs(B, T, seed=100 + T)
+    ref = go.code_generator_forward(sd, syn.VCTK_CONFIG, code, f0, spkr)
+    y = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    err = (y.cpu() - ref).abs().max().item()
+    assert err < TOL, err
+
+
+def test_int16_and_host_entry(cuda_device, vctk_gen):
+    """generate() of sr/inference.py:67-76 fused: int16 = trunc(y*32768) wrapped; host entry = same bits."""
+    gen, _ = vctk_gen
+    code, f0, spkr = syn.synthetic_inputs(2, 30, seed=5)
+    y = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device)).cpu()
+    want = (y.squeeze(1) * 32768.0).numpy().astype(np.int64).astype(np.int16)
+    got = gen.generate_int16(code.to(cuda_device), f0.to(cuda_device), spkr.to(cuda_device)).cpu().numpy()
+    assert np.array_equal(got, want)
+    yh = gen.forward_host(code.pin_memory(), f0.reshape(2, 30).contiguous().pin_memory(),
+                          spkr.reshape(2).contiguous().pin_memory())
+    assert torch.equal(yh, y.squeeze(1))
+    ih = gen.forward_host(code.pin_memory(), f0.reshape(2, 30).contiguous().pin_memory(),
+                          spkr.reshape(2).contiguous().pin_memory(), int16=True)
+    assert np.array_equal(ih.numpy(), want)
+
+
+def test_deterministic_and_batch_invariant(cuda_device, vctk_gen):
+    gen, _ = vctk_gen
+    code, f0, spkr = syn.synthetic_inputs(4, 40, seed=8)
+    a = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    b = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    assert torch.equal(a, b)
+    one = gen(code=code[2:3].to(cuda_device), f0=f0[2:3].to(cuda_device), spkr=spkr[2:3].to(cuda_device))
+    assert torch.equal(one[0], a[2])  # utterances are independent: bit-identical regardless of batch
+
+
+def test_config2_shape_properties(cuda_device, vctk_gen):
+    """BASELINE config 2 size (B=64, T=300): finite, bounded, batch rows independent of position,
+    and a sampled row equals the B=1 run bit for bit."""
+    gen, _ = vctk_gen
+    code, f0, spkr = syn.synthetic_inputs(64, 300, seed=1234)
+    y = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    assert tuple(y.shape) == (64, 1, 96000)
+    assert torch.isfinite(y).all() and y.abs().max().item() <= 1.0
+    assert 0.1 < y.std().item() < 0.6
+    for b in (0, 37, 63):
+        one = gen(code=code[b:b + 1].to(cuda_device), f0=f0[b:b + 1].to(cuda_device), spkr=spkr[b:b + 1].to(cuda_device))
+        assert torch.equal(one[0], y[b])
+
+
+def test_resblock2_and_other_geometry(cuda_device):
+    from oracle import generator_oracle as go
+    cfg = dict(syn.VCTK_CONFIG, resblock="2", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+               upsample_initial_channel=128, resblock_kernel_sizes=[3, 7, 11],
+               resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]], embedding_dim=16, model_in_dim=33)
+    sd = syn.synthetic_generator_state_dict(cfg, seed=3)
+    gen = make_generator(cfg, sd, cuda_device)
+    code, f0, spkr = syn.synthetic_inputs(2, 21, seed=4)
+    ref = go.code_generator_forward(sd, cfg, code, f0, spkr)
+    y = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    assert y.shape == ref.shape
+    assert (y.cpu() - ref).abs().max().item() < TOL
+
+
+def test_rejects_what_it_does_not_implement(cuda_device, vctk_gen):
+    from dissc_b200 import AttrDict, CodeGenerator, _lib
+    gen, _ = vctk_gen
+    code, f0, spkr = syn.synthetic_inputs(1, 5)
+    with pytest.raises(NotImplementedError):
+        gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device),
+            f0_stats=torch.zeros(1, 2, device=cuda_device))
+    with pytest.raises(_lib.DisscError):
+        gen(code=code, f0=f0, spkr=spkr)  # CPU tensors: no CPU path
+    with pytest.raises(NotImplementedError):
+        CodeGenerator(AttrDict(dict(syn.VCTK_CONFIG, lambda_commit=0.1)))
+    bad = dict(syn.VCTK_CONFIG, resblock_kernel_sizes=[3, 9, 11])
+    g2 = make_generator(bad, syn.synthetic_generator_state_dict(bad, seed=1), cuda_device)
+    with pytest.raises(_lib.DisscError, match="kernel_size=9"):
+        g2(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))

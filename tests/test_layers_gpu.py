@@ -1,0 +1,149 @@
+"""Layer-level parity: the fused sm_100a conv kernels (through the C ABI) vs the
+oracle's ATen calls (F.conv1d / F.conv_transpose1d / F.leaky_relu on CPU)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5  # fp32, different summation order than oneDNN; activations are O(1)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _conv_case(dev, B, Cin, Cout, T, k, d, pre, post, res, acc, div, lengths=None, seed=0):
+    from dissc_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    r = torch.randn(B, Cout, T, generator=g) if res else None
+    a = torch.randn(B, Cout, T, generator=g) if acc else None
+    xin = x.clone()
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xin[i, :, n:] = 0
+    y = F.leaky_relu(xin, 0.1) if pre else xin
+    y = F.conv1d(y, w, b, padding=(k * d - d) // 2, dilation=d)
+    if res:
+        y = y + r
+    if acc:
+        y = a + y
+    if div:
+        y = y / div
+    if post:
+        y = F.leaky_relu(y, 0.01)
+    xd = x.to(dev)
+    if lengths is not None:  # garbage past the valid length must be ignored by the kernel
+        for i, n in enumerate(lengths):
+            xd[i, :, n:] = float("nan")
+    out = torch.full((B, Cout, T), float("nan"), device=dev)
+    ld = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=dev)
+    rd = None if r is None else r.to(dev)
+    ad = None if a is None else a.to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dissc_conv1d_fused(_ptr(xd), _ptr(w), _ptr(b), _ptr(rd), _ptr(ad), _ptr(out), _ptr(ld), 1,
+                                                  B, Cin, Cout, T, k, d, int(pre), 0.1, int(post), 0.01,
+                                                  float(div), None))
+    torch.cuda.synchronize()
+    got = out.cpu()
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            got[i, :, n:] = 0
+            y[i, :, n:] = 0
+    assert torch.isfinite(got).all()
+    err = (got - y).abs().max().item()
+    assert err < TOL, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("C", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("k,d", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
+def test_conv1d_resblock_shapes(cuda_device, C, k, d):
+    T = {16: 2500, 32: 1300, 64: 700, 128: 300, 256: 300}[C]
+    _conv_case(cuda_device, 2, C, C, T, k, d, pre=True, post=True, res=False, acc=False, div=0)
+
+
+@pytest.mark.parametrize("k,d", [(1, 1), (5, 1), (5, 3), (7, 1), (7, 5), (11, 3), (3, 3)])
+def test_conv1d_all_instantiations(cuda_device, k, d):
+    _conv_case(cuda_device, 1, 24, 40, 333, k, d, pre=False, post=False, res=True, acc=False, div=0)
+
+
+def test_conv1d_epilogue_modes(cuda_device):
+    _conv_case(cuda_device, 3, 64, 64, 515, 7, 1, pre=False, post=False, res=True, acc=True, div=0)
+    _conv_case(cuda_device, 3, 64, 64, 515, 7, 1, pre=False, post=True, res=True, acc=True, div=3.0)
+    _conv_case(cuda_device, 1, 16, 16, 4100, 3, 1, pre=True, post=True, res=True, acc=False, div=0)
+
+
+@pytest.mark.parametrize("Cin,Cout", [(1, 1), (2, 2), (5, 3), (257, 70), (8, 130)])
+def test_conv1d_ragged_channels(cuda_device, Cin, Cout):
+    _conv_case(cuda_device, 2, Cin, Cout, 97, 7, 1, pre=False, post=False, res=False, acc=False, div=0)
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 255, 256, 257, 1025])
+def test_conv1d_ragged_time(cuda_device, T):
+    _conv_case(cuda_device, 2, 32, 32, T, 11, 5, pre=True, post=False, res=True, acc=False, div=0)
+
+
+def test_conv1d_lengths_mask(cuda_device):
+    _conv_case(cuda_device, 4, 64, 64, 600, 11, 3, pre=True, post=True, res=False, acc=False, div=0,
+               lengths=[600, 1, 257, 433])
+    _conv_case(cuda_device, 3, 16, 16, 3000, 7, 5, pre=True, post=True, res=False, acc=False, div=0,
+               lengths=[3000, 1000, 17])
+
+
+def _convt_case(dev, B, Cin, Cout, T, k, u, lengths=None, seed=0):
+    from dissc_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, k, generator=g) / (Cin * k / u) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xin = x.clone()
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xin[i, :, n:] = 0
+    y = F.conv_transpose1d(xin, w, b, stride=u, padding=(k - u) // 2)
+    xd = x.to(dev)
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xd[i, :, n:] = float("nan")
+    out = torch.full(tuple(y.shape), float("nan"), device=dev)
+    ld = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dissc_conv_transpose1d(_ptr(xd), _ptr(w), _ptr(b), _ptr(out), _ptr(ld), 1, B, Cin, Cout,
+                                                      T, k, u, None))
+    torch.cuda.synchronize()
+    got = out.cpu()
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            got[i, :, n * u:] = 0
+            y[i, :, n * u:] = 0
+    assert torch.isfinite(got).all()
+    err = (got - y).abs().max().item()
+    assert err < TOL, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("Cin,Cout,k,u,T", [
+    (512, 256, 11, 5, 50), (256, 128, 8, 4, 250), (128, 64, 8, 4, 1000), (64, 32, 4, 2, 4000),
+    (32, 16, 4, 2, 8000), (64, 32, 16, 8, 130), (4, 2, 4, 2, 33), (10, 7, 11, 5, 1), (2, 1, 8, 4, 129)])
+def test_conv_transpose1d(cuda_device, Cin, Cout, k, u, T):
+    _convt_case(cuda_device, 2, Cin, Cout, T, k, u)
+
+
+def test_conv_transpose1d_lengths(cuda_device):
+    _convt_case(cuda_device, 3, 64, 32, 300, 11, 5, lengths=[300, 1, 129])
+    _convt_case(cuda_device, 3, 32, 16, 700, 4, 2, lengths=[700, 512, 13])
+
+
+def test_unsupported_geometry_fails_loudly(cuda_device):
+    from dissc_b200 import _lib
+    x = torch.zeros(1, 4, 16, device=cuda_device)
+    w = torch.zeros(4, 4, 9)
+    out = torch.zeros(1, 4, 16, device=cuda_device)
+    rc = _lib.lib().dissc_conv1d_fused(_ptr(x), _ptr(w), None, None, None, _ptr(out), None, 1, 1, 4, 4, 16, 9, 1, 0,
+                                        0.0, 0, 0.0, 0.0, None)
+    assert rc == -2
+    assert b"kernel_size=9" in _lib.lib().dissc_last_error()
