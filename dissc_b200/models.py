@@ -308,6 +308,11 @@ class CodeGenerator(nn.Module):
             None if int16 else ptr(out), ptr(out) if int16 else None), "dissc_gen_forward_host")
         return out
 
+    def launches_per_forward(self) -> int:
+        if self._handle is None:
+            raise _lib.DisscError("no device handle yet: run a forward first")
+        return int(_lib.lib().dissc_gen_launches_per_forward(self._handle))
+
     def cost(self, B, T, device=None):
         """(algorithmic FLOPs, layer-fused-model bytes) of one (B,T) forward."""
         dev = device or self._handle_device or torch.device("cuda", 0)

@@ -1,0 +1,72 @@
+"""world_size-2 gloo test of the N>1 host logic (scatter of packed inputs, gather of per-rank
+outputs, length-balanced sharding).  The per-rank "forward" is a stand-in that tags rows with
+rank and input content -- the model itself needs a GPU and is covered by the -m gpu tests."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from dissc_b200 import dist as ddist
+    r, w, _ = ddist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    dev = torch.device("cpu")
+    B_local, T = 3, 5
+    sb = ddist.ShardedBatch(rank, world, dev)
+    if rank == 0:
+        g = torch.Generator().manual_seed(0)
+        code = torch.randint(0, 100, (world * B_local, T), generator=g)
+        f0 = torch.randn(world * B_local, T, generator=g)
+        spkr = torch.arange(world * B_local)
+        lengths = torch.randint(1, T + 1, (world * B_local,), generator=g, dtype=torch.int32)
+        c, f, s, l = sb.scatter(code, f0, spkr, lengths, B_local, T)
+    else:
+        c, f, s, l = sb.scatter(None, None, None, None, B_local, T)
+    # stand-in for the local forward: (B_local, 2) = [sum(code)+spkr, rank]
+    y = torch.stack([c.sum(1).float() + s.float(), torch.full((B_local,), float(rank))], dim=1)
+    out = sb.gather(y)
+    if rank == 0:
+        want0 = code.sum(1).float() + spkr.float()
+        assert torch.equal(out[:, 0], want0)
+        assert torch.equal(out[:, 1], torch.arange(world).repeat_interleave(B_local).float())
+        ret.put("ok")
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scatter_gather_world2():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == "ok"
+
+
+def test_pack_batch_pads_and_records_lengths():
+    from dissc_b200.dist import pack_batch
+    codes = [torch.tensor([1, 2, 3]), torch.tensor([4])]
+    f0s = [torch.tensor([0.1, 0.2, 0.3]), torch.tensor([0.4])]
+    code, f0, spkr, lengths = pack_batch(codes, f0s, [7, 9], T=4)
+    assert code.tolist() == [[1, 2, 3, 0], [4, 0, 0, 0]]
+    assert lengths.tolist() == [3, 1] and spkr.tolist() == [7, 9]
+    assert f0[0, :3].tolist() == [0.1, 0.2, 0.3] or torch.allclose(f0[0, :3], torch.tensor([0.1, 0.2, 0.3]))
