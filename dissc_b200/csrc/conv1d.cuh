@@ -114,7 +114,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_fused_kernel(const ConvPar
             }
           } else {
             v = __ldg(p.in + ((size_t)b * p.Cin + ci) * p.T + t);
-            if (p.pre_act) v = leaky(v, p.pre_slope);
           }
         }
       }
@@ -126,7 +125,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_fused_kernel(const ConvPar
 #pragma unroll
     for (int i = 0; i < C::NX; ++i) {
       const int e = tid + i * kThreads;
-      if (e < C::X_CHUNK) dst[e] = xr[i];
+      // leaky-relu applied here, after the FMA loop, so the global load's latency hides behind it
+      if (e < C::X_CHUNK) dst[e] = p.pre_act ? leaky(xr[i], p.pre_slope) : xr[i];
     }
   };
 

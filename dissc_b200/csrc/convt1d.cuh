@@ -13,6 +13,8 @@
 // lanes (conflict-free shared-memory reads).  Weight chunks arrive by 1-D bulk
 // TMA, activation rows are staged through registers, double-buffered.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dissc {
@@ -26,6 +28,12 @@ struct ConvTParams {
   int len_mul;         // valid input frames = lengths[b]*len_mul
   int B, Cin, Cout, Tin, Tout;
   int pad;
+  // tensor-core stage hand-off (conv1d_tc.cuh layouts); when out_f32b != null `out` is unused:
+  float* out_f32b;     // raw x_up, fp32 [B][Cout/8][Tr][8]
+  __half* out_hi;      // leaky_relu(x_up, plane_slope) split into fp16 planes [B][Cout/8][Tp][8]
+  __half* out_lo;
+  int Tr, Tp, halo;
+  float plane_slope;
 };
 
 template <int CO_TILE, int KW, int U, int CI_CHUNK>
@@ -59,7 +67,8 @@ __global__ void __launch_bounds__(kThreads, 2) convt1d_kernel(const ConvTParams 
   const int co_tile = blockIdx.y;
   const int q0 = blockIdx.x * C::F_TILE;
   const int Tvalid = p.lengths ? min(p.Tin, p.lengths[b] * p.len_mul) : p.Tin;
-  if (q0 - (C::M - 1) >= Tvalid && q0 > 0) return;  // reads only padding; outputs never consumed
+  // reads only padding; outputs never consumed (the tensor-core hand-off needs its zeros written, so no exit there)
+  if (q0 - (C::M - 1) >= Tvalid && q0 > 0 && !p.out_f32b) return;
   const int nchunks = (p.Cin + CI_CHUNK - 1) / CI_CHUNK;
   const float* wbase = p.w + (size_t)co_tile * nchunks * C::W_CHUNK;
 
@@ -152,6 +161,43 @@ __global__ void __launch_bounds__(kThreads, 2) convt1d_kernel(const ConvTParams 
   }
 
   const int co_base = co_tile * CO_TILE + cg * C::RCO;
+  if (p.out_f32b) {
+    // blocked hand-off: this thread's 4 consecutive channels are one 16 B (fp32) / 8 B (fp16) store per time step
+    if (co_base + C::RCO > p.Cout) return;  // Cout % 16 == 0 in this mode
+    float bv[C::RCO];
+#pragma unroll
+    for (int cc = 0; cc < C::RCO; ++cc) bv[cc] = p.bias ? __ldg(p.bias + co_base + cc) : 0.f;
+    const int Tv_out = p.lengths ? min(p.Tout, Tvalid * U) : p.Tout;
+    const size_t slab = (size_t)b * (p.Cout / 8) + co_base / 8;
+    const int sub = co_base & 7;
+#pragma unroll
+    for (int f = 0; f < C::RF; ++f) {
+      const int q = q0 + tl + f * C::TT;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = q * U + u - p.pad;
+        if (t < 0 || t >= p.Tout) continue;
+        float v[C::RCO];
+#pragma unroll
+        for (int cc = 0; cc < C::RCO; ++cc) v[cc] = acc[cc][f][u] + bv[cc];
+        const bool valid = t < Tv_out;
+        if (valid) *reinterpret_cast<float4*>(p.out_f32b + (slab * p.Tr + t) * 8 + sub) = make_float4(v[0], v[1], v[2], v[3]);
+        __align__(8) __half h[4];
+        __align__(8) __half l[4];
+#pragma unroll
+        for (int cc = 0; cc < C::RCO; ++cc) {
+          float a = valid ? leaky(v[cc], p.plane_slope) : 0.f;
+          a = fminf(fmaxf(a, -65504.f), 65504.f);
+          h[cc] = __float2half_rn(a);
+          l[cc] = __float2half_rn(a - __half2float(h[cc]));
+        }
+        const size_t po = (slab * p.Tp + p.halo + t) * 8 + sub;
+        *reinterpret_cast<uint2*>(p.out_hi + po) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(p.out_lo + po) = *reinterpret_cast<const uint2*>(l);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int cc = 0; cc < C::RCO; ++cc) {
     const int co = co_base + cc;

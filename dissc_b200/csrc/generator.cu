@@ -10,6 +10,8 @@
 //           ... last m: MRF accumulate folded in: j==0 -> xs, j>0 -> xs += , last j -> lrelu((xs+v)/n_rk) -> act
 //   conv_post + tanh                                        -> out
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -17,6 +19,7 @@
 
 #include "common.cuh"
 #include "conv1d.cuh"
+#include "conv1d_tc.cuh"
 #include "conv_post.cuh"
 #include "convt1d.cuh"
 
@@ -155,6 +158,122 @@ static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------
+// tensor-core path: plan + weight packing + launch
+// ------------------------------------------------------------------------
+struct TcLayer {
+  bool ok = false;
+  int C = 0, k = 0, dil = 1, pad = 0;
+  int KB = 0, n_cb = 0, JG = 0, SPC = 0, NS = 0, resident = 0, tmem_cols = 0, nbuf = 1;
+  size_t smem = 0;
+  __half* w = nullptr;  // packed [cb][k][2][KB/8][N][8], device
+  float inv_scale = 1.f;
+};
+
+constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // 227 KB per CTA minus the kernel's static shared memory
+
+static bool tc_plan(int C, int k, int dil, TcLayer* L) {
+  L->ok = false;
+  if (C % 16 != 0 || C < 16 || C > 256) return false;
+  const int pad = (k * dil - dil) / 2;
+  if (pad > kTcHalo || k < 1) return false;
+  L->C = C; L->k = k; L->dil = dil; L->pad = pad;
+  L->KB = C >= 32 ? 32 : 16;
+  L->n_cb = C / L->KB;
+  const int R = 128 + (k - 1) * dil;
+  const size_t a_bytes = (size_t)4 * L->KB * R;
+  const size_t w_tap = (size_t)4 * L->KB * C;
+  L->JG = (int)std::min<size_t>(std::max<size_t>(32768 / w_tap, 1), k);
+  L->SPC = (k + L->JG - 1) / L->JG;
+  const size_t slot = (size_t)L->JG * w_tap;
+  const int total_slots = L->n_cb * L->SPC;
+  const size_t misc = (size_t)((C + 1) & ~1) * 4 + 256;
+  if ((size_t)total_slots * slot <= 96 * 1024 && total_slots <= kTcMaxStages) {
+    L->resident = 1;
+    L->NS = total_slots;
+  } else {
+    L->resident = 0;
+    const size_t avail = kMaxDynSmem - 2 * a_bytes - misc - 8 * 20;
+    L->NS = (int)std::min<size_t>(8, avail / (slot + 16));
+    if (L->NS < 2) return false;
+  }
+  L->smem = 2 * a_bytes + (size_t)L->NS * slot + misc + (size_t)(8 + 2 * L->NS) * 8;
+  if (L->smem > kMaxDynSmem) return false;
+  L->nbuf = (4 * C <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < L->nbuf * 2 * C) cols *= 2;
+  L->tmem_cols = cols;
+  L->ok = true;
+  return true;
+}
+
+// w: (Cout=N, Cin, k) fp32 -> fp16 hi/lo planes of w*2^s, layout [cb][k][2][KB/8][N][8]
+static std::vector<__half> pack_weights_tc(const float* w, int C, int k, int KB, float* inv_scale) {
+  float mx = 0.f;
+  for (size_t i = 0; i < (size_t)C * C * k; ++i) mx = std::max(mx, std::fabs(w[i]));
+  int s = 0;
+  if (mx > 0.f) {
+    int e;
+    std::frexp(mx, &e);  // mx = f * 2^e, f in [0.5,1)
+    s = 4 - e;           // mx * 2^s in [8,16)
+    s = std::max(-14, std::min(24, s));
+  }
+  const float scale = std::ldexp(1.f, s);
+  *inv_scale = std::ldexp(1.f, -s);
+  const int n_cb = C / KB;
+  std::vector<__half> out((size_t)n_cb * k * 2 * (KB / 8) * C * 8);
+  for (int cb = 0; cb < n_cb; ++cb)
+    for (int j = 0; j < k; ++j)
+      for (int c8 = 0; c8 < KB / 8; ++c8)
+        for (int n = 0; n < C; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const int ci = cb * KB + c8 * 8 + e;
+            const float v = w[((size_t)n * C + ci) * k + j] * scale;
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            const size_t base = ((size_t)cb * k + j) * 2;
+            out[(((base + 0) * (KB / 8) + c8) * C + n) * 8 + e] = h;
+            out[(((base + 1) * (KB / 8) + c8) * C + n) * 8 + e] = l;
+          }
+  return out;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int launch_conv_tc(TcConvParams p, const TcLayer& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DISSC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    attr_set = true;
+  }
+  p.k = L.k; p.dil = L.dil; p.pad = L.pad; p.KB = L.KB; p.n_cb = L.n_cb; p.JG = L.JG; p.SPC = L.SPC; p.NS = L.NS;
+  p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.nbuf = L.nbuf; p.w = L.w; p.w_inv_scale = L.inv_scale;
+  p.Cin = L.C; p.N = L.C;
+  p.tiles_per_b = p.Tr / 128;
+  p.n_tiles = p.B * p.tiles_per_b;
+  const int grid = std::min(p.n_tiles, num_sms());
+  conv1d_tc_kernel<<<grid, kTcThreads, L.smem, st>>>(p);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+static int launch_zero_halos(__half* hi, __half* lo, int slabs, int Tp, int T, cudaStream_t st) {
+  const long long total = (long long)slabs * (Tp - T);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  tc_zero_halos_kernel<<<std::max(blocks, 1), 256, 0, st>>>(hi, lo, slabs, Tp, T);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+// ------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------
 struct ConvLayer {
@@ -191,6 +310,10 @@ struct dissc_gen {
   ConvTLayer ups[DISSC_MAX_STAGES];
   // rb[stage][j][m][0|1]  (ResBlock2 uses only [0])
   ConvLayer rb[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS][2];
+  // tensor-core twins of rb[][][][] and per-stage eligibility
+  TcLayer rb_tc[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS][2];
+  bool stage_tc[DISSC_MAX_STAGES] = {};
+  int use_tc = 1;
   float* dict_w = nullptr;
   float* spkr_w = nullptr;
   int n_launches = 0;
@@ -238,6 +361,18 @@ static int make_conv(dissc_gen* g, const WeightMap& wm, const std::string& prefi
   return dev_upload(g, b->data, Cout, &L->bias);
 }
 
+static int make_conv_tc(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int C, int k, int dil, TcLayer* L) {
+  if (!tc_plan(C, k, dil, L)) return DISSC_OK;  // not eligible: the fp32 CUDA-core kernel handles it
+  const dissc_tensor* w = wm.get(prefix + ".weight");
+  auto packed = pack_weights_tc(w->data, C, k, L->KB, &L->inv_scale);
+  __half* d = nullptr;
+  DISSC_CUDA(cudaMalloc(&d, packed.size() * sizeof(__half)));
+  g->allocs.push_back(d);
+  DISSC_CUDA(cudaMemcpy(d, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  L->w = d;
+  return DISSC_OK;
+}
+
 static int make_convt(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int Cin, int Cout, int k, int u,
                       ConvTLayer* L) {
   const dissc_tensor* w = wm.get(prefix + ".weight");
@@ -257,19 +392,22 @@ static int make_convt(dissc_gen* g, const WeightMap& wm, const std::string& pref
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// elements of the largest activation a (B,T) forward materialises
-static size_t max_act_elems(const dissc_gen* g, int B, int T) {
-  size_t mx = (size_t)B * g->cfg.c0 * T;
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// bytes of one workspace region: large enough for any stage's tensor in any layout
+// (plain (B,C,T) fp32, blocked f32b [B][C/8][Tr][8] fp32, or an fp16 hi+lo plane pair [B][C/8][Tp][8] x2)
+static size_t region_bytes(const dissc_gen* g, int B, int T) {
+  size_t mx = (size_t)B * g->cfg.c0 * T * 4;
   size_t t = T;
-  int ch = g->cfg.c0;
   for (int i = 0; i < g->cfg.n_up; ++i) {
     const ConvTLayer& U = g->ups[i];
     t = (t - 1) * U.u - 2 * U.pad + U.k;
-    ch = U.Cout;
-    mx = std::max(mx, (size_t)B * ch * t);
+    const size_t tp = round_up(t, 128) + 2 * kTcHalo;
+    mx = std::max(mx, (size_t)B * round_up(U.Cout, 8) * tp * 4);
   }
-  return mx;
+  return round_up(mx, 1024);
 }
+constexpr int kNumRegions = 8;
 
 static int out_len(const dissc_gen* g, int T) {
   long t = T;
@@ -325,12 +463,21 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
   DISSC_CUDA(cudaGetDevice(&dev));
   DISSC_CHECK(dev == g->device, DISSC_EINVAL, "current device %d != handle device %d", dev, g->device);
 
-  const size_t smax = align_up(max_act_elems(g, B, T) * sizeof(float), 256);
+  const size_t RS = region_bytes(g, B, T);
   char* wsb = static_cast<char*>(workspace);
-  float* act[2] = {reinterpret_cast<float*>(wsb), reinterpret_cast<float*>(wsb + smax)};
-  float* x_up = reinterpret_cast<float*>(wsb + 2 * smax);
-  float* xt = reinterpret_cast<float*>(wsb + 3 * smax);
-  float* r = reinterpret_cast<float*>(wsb + 4 * smax);
+  auto region = [&](int i) { return wsb + (size_t)i * RS; };
+  float* act[2] = {reinterpret_cast<float*>(region(0)), reinterpret_cast<float*>(region(1))};
+  // CUDA-core stages: x_up / xt / r are plain (B,C,T) fp32 in regions 2,3,4.
+  // Tensor-core stages: F_up, F_r, F_xs (blocked fp32) in 2,4,5; plane pairs P_xt, P_up, P_r in 3,6,7.
+  float* x_up = reinterpret_cast<float*>(region(2));
+  float* xt = reinterpret_cast<float*>(region(3));
+  float* r = reinterpret_cast<float*>(region(4));
+  float* F_up = x_up;
+  float* F_r = r;
+  float* F_xs = reinterpret_cast<float*>(region(5));
+  struct Planes { __half* hi; __half* lo; };
+  auto planes = [&](int i) { return Planes{reinterpret_cast<__half*>(region(i)), reinterpret_cast<__half*>(region(i) + RS / 2)}; };
+  const Planes P_xt = planes(3), P_up = planes(6), P_r = planes(7);
 
   Launcher L{st, prof};
   const dissc_gen_cfg& c = g->cfg;
@@ -357,17 +504,33 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     DISSC_TRY(L.end());
   }
 
-  int cur = 0;     // act[cur] holds the (already activated) stage input
+  int cur = 0;     // act[cur] holds the (already activated) stage input, plain (B,C,T)
   int Tcur = T;    // time steps at the current rate
   int mul = 1;     // valid length multiplier (product of rates so far)
   for (int i = 0; i < c.n_up; ++i) {
     const ConvTLayer& U = g->ups[i];
     const int Tout = (Tcur - 1) * U.u - 2 * U.pad + U.k;
+    const bool tc = g->use_tc && g->stage_tc[i];
+    const int Tr = (int)round_up(Tout, 128), Tp = Tr + 2 * kTcHalo;
+    const int ch = U.Cout;
+    if (tc) {
+      // zero padding of the three plane pairs this stage uses (halo rows + round-up rows)
+      DISSC_TRY(L.begin("zero_halos", 0));
+      DISSC_TRY(launch_zero_halos(P_up.hi, P_up.lo, B * ch / 8, Tp, Tout, st));
+      DISSC_TRY(launch_zero_halos(P_xt.hi, P_xt.lo, B * ch / 8, Tp, Tout, st));
+      DISSC_TRY(launch_zero_halos(P_r.hi, P_r.lo, B * ch / 8, Tp, Tout, st));
+      DISSC_TRY(L.end());
+      L.count += 2;
+    }
     {
       ConvTParams p{};
       p.in = act[cur]; p.w = U.w; p.bias = U.bias; p.out = x_up;
       p.lengths = lengths; p.len_mul = mul;
       p.B = B; p.Cin = U.Cin; p.Cout = U.Cout; p.Tin = Tcur; p.Tout = Tout; p.pad = U.pad;
+      if (tc) {
+        p.out = nullptr; p.out_f32b = F_up; p.out_hi = P_up.hi; p.out_lo = P_up.lo;
+        p.Tr = Tr; p.Tp = Tp; p.halo = kTcHalo; p.plane_slope = 0.1f;
+      }
       snprintf(name, sizeof(name), "ups.%d", i);
       DISSC_TRY(L.begin(name, 2.0 * U.Cin * U.Cout * U.k * (double)Tcur * B));
       DISSC_TRY(launch_convt(p, U.k, U.u, U.co_tile, st));
@@ -375,19 +538,57 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     }
     Tcur = Tout;
     mul *= U.u;
-    const int ch = U.Cout;
-    float* xs = act[cur ^ 1];  // MRF accumulator; becomes the next stage's activated input
+    float* xs = act[cur ^ 1];  // MRF accumulator (CUDA-core path) / next stage's activated input
     const bool last_stage = (i == c.n_up - 1);
     const float next_slope = last_stage ? 0.01f : 0.1f;  // sr/models.py:110 vs :101
     for (int j = 0; j < c.n_rk; ++j) {
       for (int m = 0; m < c.n_dil; ++m) {
         const bool last_m = (m == c.n_dil - 1);
+        const bool last_j = (j == c.n_rk - 1);
+        const ConvLayer& c1 = g->rb[i][j][m][0];
+        const double fl = 2.0 * ch * ch * (double)c1.k * Tcur * B;
+        if (tc) {
+          const Planes rin_p = (m == 0) ? P_up : P_r;
+          const float* rin_f = (m == 0) ? F_up : F_r;
+          TcConvParams base{};
+          base.lengths = lengths; base.len_mul = mul;
+          base.B = B; base.T = Tcur; base.Tr = Tr; base.Tp = Tp;
+          if (c.resblock == 1) {
+            // K3: (leaky-relu'd planes) -> dilated conv -> leaky-relu -> planes   (sr/models.py:36-38)
+            TcConvParams p = base;
+            p.a_hi = rin_p.hi; p.a_lo = rin_p.lo; p.bias = c1.bias;
+            p.out_hi = P_xt.hi; p.out_lo = P_xt.lo; p.plane_act = 1; p.plane_slope = 0.1f;
+            snprintf(name, sizeof(name), "s%d.rb%d.c1.%d.tc", i, j, m);
+            DISSC_TRY(L.begin(name, fl));
+            DISSC_TRY(launch_conv_tc(p, g->rb_tc[i][j][m][0], st));
+            DISSC_TRY(L.end());
+          }
+          // K4: conv -> + residual [-> MRF accumulate]   (:39-40, :104-109)
+          const int which = (c.resblock == 1) ? 1 : 0;
+          TcConvParams q = base;
+          const Planes qin = (c.resblock == 1) ? P_xt : rin_p;
+          q.a_hi = qin.hi; q.a_lo = qin.lo; q.bias = g->rb[i][j][m][which].bias; q.res = rin_f;
+          if (!last_m) {
+            q.out_f32b = F_r; q.out_hi = P_r.hi; q.out_lo = P_r.lo; q.plane_act = 1; q.plane_slope = 0.1f;
+          } else {
+            if (j > 0) q.acc_in = F_xs;
+            if (!last_j) {
+              q.out_f32b = F_xs;
+            } else {
+              q.div = (float)c.n_rk;
+              q.out_plain = xs; q.plain_act = 1; q.plain_slope = next_slope;
+            }
+          }
+          snprintf(name, sizeof(name), "s%d.rb%d.c2.%d.tc", i, j, m);
+          DISSC_TRY(L.begin(name, fl));
+          DISSC_TRY(launch_conv_tc(q, g->rb_tc[i][j][m][which], st));
+          DISSC_TRY(L.end());
+          continue;
+        }
         const float* rin = (m == 0) ? x_up : r;
         ConvParams p{};
         p.lengths = lengths; p.len_mul = mul;
         p.B = B; p.Cin = ch; p.Cout = ch; p.T = Tcur;
-        const ConvLayer& c1 = g->rb[i][j][m][0];
-        const double fl = 2.0 * ch * ch * (double)c1.k * Tcur * B;
         if (c.resblock == 1) {
           // K3: lrelu -> dilated conv -> lrelu     (sr/models.py:36-38)
           p.in = rin; p.w = c1.w; p.bias = c1.bias; p.out = xt; p.pad = c1.pad;
@@ -413,7 +614,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
         } else {
           q.out = xs;
           if (j > 0) q.acc_in = xs;
-          if (j == c.n_rk - 1) {
+          if (last_j) {
             q.div = (float)c.n_rk;
             q.post_act = 1; q.post_slope = next_slope;
           }
@@ -496,11 +697,25 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
             return fail(rc);
           if ((rc = make_conv(g, wm, p + ".convs2." + std::to_string(m), ch, ch, c.rk[j], 1, &g->rb[i][j][m][1])))
             return fail(rc);
+          if ((rc = make_conv_tc(g, wm, p + ".convs1." + std::to_string(m), ch, c.rk[j], c.dil[j][m],
+                                 &g->rb_tc[i][j][m][0])))
+            return fail(rc);
+          if ((rc = make_conv_tc(g, wm, p + ".convs2." + std::to_string(m), ch, c.rk[j], 1, &g->rb_tc[i][j][m][1])))
+            return fail(rc);
         } else {
           if ((rc = make_conv(g, wm, p + ".convs." + std::to_string(m), ch, ch, c.rk[j], c.dil[j][m],
                               &g->rb[i][j][m][0])))
             return fail(rc);
+          if ((rc = make_conv_tc(g, wm, p + ".convs." + std::to_string(m), ch, c.rk[j], c.dil[j][m],
+                                 &g->rb_tc[i][j][m][0])))
+            return fail(rc);
         }
+      }
+    // a stage runs on the tensor cores iff every one of its convs has a tcgen05 plan
+    g->stage_tc[i] = true;
+    for (int j = 0; j < c.n_rk; ++j)
+      for (int m = 0; m < c.n_dil; ++m) {
+        g->stage_tc[i] = g->stage_tc[i] && g->rb_tc[i][j][m][0].ok && (c.resblock != 1 || g->rb_tc[i][j][m][1].ok);
       }
   }
   // conv_post: (1, ch, 7) -> plain (ch, 7)
@@ -526,6 +741,7 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
     }
   }
   g->n_launches = 1 + c.n_up * (1 + c.n_rk * c.n_dil * (c.resblock == 1 ? 2 : 1)) + 1;
+  if (const char* e = getenv("DISSC_TC")) g->use_tc = atoi(e) != 0;
   *out = g;
   return DISSC_OK;
 }
@@ -540,11 +756,24 @@ void dissc_gen_destroy(dissc_gen_t* g) {
 }
 
 int dissc_gen_hop(const dissc_gen_t* g) { return g ? g->hop : 0; }
+
+int dissc_gen_set_tensor_cores(dissc_gen_t* g, int enable) {
+  DISSC_CHECK(g, DISSC_EINVAL, "null handle");
+  g->use_tc = enable != 0;
+  return DISSC_OK;
+}
+
+int dissc_gen_tensor_core_stages(const dissc_gen_t* g) {
+  if (!g || !g->use_tc) return 0;
+  int n = 0;
+  for (int i = 0; i < g->cfg.n_up; ++i) n += g->stage_tc[i] ? 1 : 0;
+  return n;
+}
 int dissc_gen_launches_per_forward(const dissc_gen_t* g) { return g ? g->n_launches : 0; }
 
 int dissc_gen_workspace_bytes(const dissc_gen_t* g, int B, int T, size_t* bytes) {
   DISSC_CHECK(g && bytes && B > 0 && T > 0, DISSC_EINVAL, "bad argument");
-  *bytes = 5 * align_up(max_act_elems(g, B, T) * sizeof(float), 256);
+  *bytes = kNumRegions * region_bytes(g, B, T);
   return DISSC_OK;
 }
 
@@ -711,6 +940,75 @@ int dissc_conv_transpose1d(const float* in, const float* w_host, const float* bi
   if (db) cudaFree(db);
   if (rc) return rc;
   DISSC_CUDA(e);
+  return DISSC_OK;
+}
+
+int dissc_conv1d_tc(const float* in, const float* w_host, const float* bias_host, const float* res,
+                    const float* acc_in, float* out_plain, float* out_raw, float* out_planes, const int32_t* lengths,
+                    int len_mul, int B, int C, int T, int k, int dilation, int pre_act, float pre_slope, int post_act,
+                    float post_slope, float div, void* stream) {
+  DISSC_CHECK(in && w_host && B > 0 && C > 0 && T > 0, DISSC_EINVAL, "bad argument");
+  TcLayer L;
+  DISSC_CHECK(tc_plan(C, k, dilation, &L), DISSC_EUNSUPPORTED,
+              "no tcgen05 plan for C=%d kernel_size=%d dilation=%d (needs C%%16==0, 16<=C<=256, pad<=%d)", C, k,
+              dilation, kTcHalo);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Tr = (int)round_up(T, 128), Tp = Tr + 2 * kTcHalo;
+  const size_t plane_elems = (size_t)B * (C / 8) * Tp * 8, f_elems = (size_t)B * (C / 8) * Tr * 8;
+  auto packed = pack_weights_tc(w_host, C, k, L.KB, &L.inv_scale);
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    tmp.push_back(d);
+    return d;
+  };
+  auto cleanup = [&]() { for (void* d : tmp) cudaFree(d); };
+  __half* dw = (__half*)dalloc(packed.size() * 2);
+  float* db = (float*)dalloc((size_t)C * 4);
+  __half* a_hi = (__half*)dalloc(plane_elems * 2);
+  __half* a_lo = (__half*)dalloc(plane_elems * 2);
+  __half* o_hi = (__half*)dalloc(plane_elems * 2);
+  __half* o_lo = (__half*)dalloc(plane_elems * 2);
+  float* f_res = (float*)dalloc(f_elems * 4);
+  float* f_acc = (float*)dalloc(f_elems * 4);
+  float* f_out = (float*)dalloc(f_elems * 4);
+  if (!dw || !db || !a_hi || !a_lo || !o_hi || !o_lo || !f_res || !f_acc || !f_out) {
+    cleanup();
+    return set_err(DISSC_ENOMEM, "cudaMalloc failed in dissc_conv1d_tc");
+  }
+  cudaMemcpyAsync(dw, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, st);
+  std::vector<float> zero_bias(C, 0.f);
+  cudaMemcpyAsync(db, bias_host ? bias_host : zero_bias.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st);
+  // garbage everywhere first: the kernel must not depend on anything but the zeroed halos
+  cudaMemsetAsync(a_hi, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(a_lo, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
+  const int nb = 148 * 4;
+  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, C, T, Tp, pre_act, pre_slope);
+  int rc = launch_zero_halos(a_hi, a_lo, B * C / 8, Tp, T, st);
+  if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * C / 8, Tp, T, st);
+  if (res) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(res, f_res, B, C, T, Tr);
+  if (acc_in) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(acc_in, f_acc, B, C, T, Tr);
+  L.w = dw;
+  TcConvParams p{};
+  p.a_hi = a_hi; p.a_lo = a_lo; p.bias = db;
+  p.res = res ? f_res : nullptr; p.acc_in = acc_in ? f_acc : nullptr;
+  p.out_f32b = out_raw ? f_out : nullptr;
+  p.out_hi = out_planes ? o_hi : nullptr; p.out_lo = out_planes ? o_lo : nullptr;
+  p.out_plain = out_plain;
+  p.lengths = lengths; p.len_mul = len_mul;
+  p.B = B; p.T = T; p.Tr = Tr; p.Tp = Tp;
+  p.div = div; p.plane_act = post_act; p.plane_slope = post_slope; p.plain_act = post_act; p.plain_slope = post_slope;
+  if (!rc) rc = launch_conv_tc(p, L, st);
+  if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, C, T, Tr);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cleanup();
+  if (rc) return rc;
+  DISSC_CUDA(e);
+  DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
 

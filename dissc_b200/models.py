@@ -308,6 +308,13 @@ class CodeGenerator(nn.Module):
             None if int16 else ptr(out), ptr(out) if int16 else None), "dissc_gen_forward_host")
         return out
 
+    def set_tensor_cores(self, enable: bool, device=None) -> int:
+        """Toggle the tcgen05 path (default on); returns how many stages now run on tensor cores."""
+        dev = device or self._handle_device or torch.device("cuda", 0)
+        h = self._ensure_handle(dev)
+        _lib.check(_lib.lib().dissc_gen_set_tensor_cores(h, int(bool(enable))))
+        return int(_lib.lib().dissc_gen_tensor_core_stages(h))
+
     def launches_per_forward(self) -> int:
         if self._handle is None:
             raise _lib.DisscError("no device handle yet: run a forward first")

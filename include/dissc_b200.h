@@ -118,6 +118,12 @@ int dissc_gen_forward_i16(dissc_gen_t* g, const int64_t* code, const float* f0, 
 int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
                            const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16);
 
+/* The ResBlock stages whose geometry allows it (C % 16 == 0, 16 <= C <= 256, padding <= 32) run on the
+ * tcgen05 tensor cores with split-fp16 operands (fp32-accurate); the others, and
+ * everything when disabled, use the fp32 CUDA-core kernels.  Default: enabled (env DISSC_TC=0 disables). */
+int dissc_gen_set_tensor_cores(dissc_gen_t* g, int enable);
+int dissc_gen_tensor_core_stages(const dissc_gen_t* g); /* how many stages currently take the tensor-core path */
+
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
 int dissc_gen_launches_per_forward(const dissc_gen_t* g);
 
@@ -149,6 +155,15 @@ int dissc_conv1d_fused(const float* in, const float* w_host, const float* bias_h
 int dissc_conv_transpose1d(const float* in, const float* w_host, const float* bias_host, float* out,
                            const int32_t* lengths, int len_mul, int B, int Cin, int Cout, int T_in, int k, int u,
                            void* stream);
+
+/* Tensor-core twin of dissc_conv1d_fused (Cin == Cout == C).  Plain (B,C,T) fp32 device tensors in and out;
+ * the entry point converts to/from the blocked tensor-core layouts itself (test entry, not a fast path).
+ * Any of out_plain (post-activated), out_raw (value before post), out_planes (fp16 hi+lo of the
+ * post-activated value, summed back to fp32) may be NULL. */
+int dissc_conv1d_tc(const float* in, const float* w_host, const float* bias_host, const float* res,
+                    const float* acc_in, float* out_plain, float* out_raw, float* out_planes, const int32_t* lengths,
+                    int len_mul, int B, int C, int T, int k, int dilation, int pre_act, float pre_slope, int post_act,
+                    float post_slope, float div, void* stream);
 
 const char* dissc_last_error(void);
 const char* dissc_version(void);

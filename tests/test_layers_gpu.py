@@ -147,3 +147,93 @@ def test_unsupported_geometry_fails_loudly(cuda_device):
                                         0.0, 0, 0.0, 0.0, None)
     assert rc == -2
     assert b"kernel_size=9" in _lib.lib().dissc_last_error()
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, split-fp16) twin of the fused conv
+# ---------------------------------------------------------------------------------------------
+def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0, wscale=1.0):
+    from dissc_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, T, generator=g)
+    w = wscale * torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b = torch.randn(C, generator=g)
+    r = torch.randn(B, C, T, generator=g) if res else None
+    a = torch.randn(B, C, T, generator=g) if acc else None
+    xin = x.clone()
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xin[i, :, n:] = 0
+    y = F.leaky_relu(xin, 0.1) if pre else xin
+    y = F.conv1d(y.double(), w.double(), b.double(), padding=(k * d - d) // 2, dilation=d).float()
+    if res:
+        y = y + r
+    if acc:
+        y = a + y
+    if div:
+        y = y / div
+    raw = y.clone()
+    if post:
+        y = F.leaky_relu(y, 0.01)
+    xd = x.to(dev)
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xd[i, :, n:] = float("nan")
+    outs = [torch.full((B, C, T), float("nan"), device=dev) for _ in range(3)]
+    ld = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=dev)
+    rd = None if r is None else r.to(dev)
+    ad = None if a is None else a.to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dissc_conv1d_tc(_ptr(xd), _ptr(w), _ptr(b), _ptr(rd), _ptr(ad), _ptr(outs[0]),
+                                               _ptr(outs[1]), _ptr(outs[2]), _ptr(ld), 1, B, C, T, k, d, int(pre), 0.1,
+                                               int(post), 0.01, float(div), None))
+    torch.cuda.synchronize()
+    scale = max(1.0, wscale)
+    for name, got, want, tol in (("plain", outs[0].cpu(), y, 2e-5), ("raw", outs[1].cpu(), raw, 2e-5),
+                                 ("planes", outs[2].cpu(), y, 2e-5)):
+        got = got.clone()
+        want = want.clone()
+        if lengths is not None:
+            for i, n in enumerate(lengths):
+                if name == "planes":
+                    assert torch.all(got[i, :, n:] == 0), "rows past the valid length must be stored as zeros"
+                got[i, :, n:] = 0
+                want[i, :, n:] = 0
+        assert torch.isfinite(got).all(), name
+        err = (got - want).abs().max().item()
+        assert err < tol * scale, f"{name}: max abs err {err}"
+
+
+@pytest.mark.parametrize("C", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("k,d", [(3, 1), (3, 5), (7, 3), (11, 1), (11, 5)])
+def test_tc_conv_resblock_shapes(cuda_device, C, k, d):
+    T = {16: 2500, 32: 1300, 64: 700, 128: 300, 256: 300}[C]
+    _tc_case(cuda_device, 2, C, T, k, d, pre=True, post=True, res=False, acc=False, div=0)
+
+
+def test_tc_conv_epilogue_modes(cuda_device):
+    _tc_case(cuda_device, 3, 64, 515, 7, 1, pre=False, post=False, res=True, acc=True, div=0)
+    _tc_case(cuda_device, 3, 64, 515, 7, 1, pre=False, post=True, res=True, acc=True, div=3.0)
+    _tc_case(cuda_device, 1, 16, 4100, 3, 1, pre=True, post=True, res=True, acc=False, div=0)
+
+
+@pytest.mark.parametrize("T", [1, 2, 127, 128, 129, 1025])
+def test_tc_conv_ragged_time(cuda_device, T):
+    _tc_case(cuda_device, 2, 32, T, 11, 5, pre=True, post=False, res=True, acc=False, div=0)
+
+
+def test_tc_conv_many_tiles_persistent(cuda_device):
+    # more tiles than SMs: every CTA loops, both TMEM accumulators and all pipeline phases wrap
+    _tc_case(cuda_device, 8, 128, 128 * 45, 7, 3, pre=True, post=True, res=True, acc=False, div=0)
+    _tc_case(cuda_device, 8, 16, 128 * 90, 11, 5, pre=True, post=True, res=False, acc=False, div=0)
+
+
+def test_tc_conv_lengths_mask(cuda_device):
+    _tc_case(cuda_device, 4, 64, 600, 11, 3, pre=True, post=True, res=False, acc=False, div=0,
+             lengths=[600, 1, 257, 433])
+
+
+@pytest.mark.parametrize("wscale", [1e-3, 1.0, 300.0])
+def test_tc_conv_weight_scaling(cuda_device, wscale):
+    # the power-of-two pre-scale keeps the fp16 split accurate whatever the weight magnitude
+    _tc_case(cuda_device, 1, 64, 300, 7, 1, pre=False, post=False, res=False, acc=False, div=0, wscale=wscale)
