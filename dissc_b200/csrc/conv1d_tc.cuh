@@ -61,6 +61,7 @@ struct TcConvParams {
   int resident;   // 1: NS == n_cb*SPC, weights loaded once per CTA
   int tiles_per_b, n_tiles;
   int tmem_cols;  // allocation (power of two >= nbuf*2*N)
+  int NA;         // activation-block buffers in shared memory (2..4)
   int nbuf;       // TMEM tile buffers (2 when 4*N <= 512, else 1); each holds a main and a cross accumulator
   float div;
   int plane_act, plain_act;
@@ -118,23 +119,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvPa
   const uint32_t w_tap_bytes = 2 * w_plane_bytes;
   const uint32_t w_slot_bytes = (uint32_t)p.JG * w_tap_bytes;
   unsigned char* sA = smem_raw;
-  unsigned char* sW = sA + 2 * a_bytes;
+  unsigned char* sW = sA + (size_t)p.NA * a_bytes;
   float* s_bias = reinterpret_cast<float*>(sW + (size_t)p.NS * w_slot_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + ((p.N + 1) & ~1));
-  uint64_t* a_full = bars;            // [2]
-  uint64_t* a_empty = bars + 2;       // [2]
-  uint64_t* acc_full = bars + 4;      // [2]
-  uint64_t* acc_empty = bars + 6;     // [2]
-  uint64_t* w_full = bars + 8;        // [NS]
+  uint64_t* a_full = bars;            // [4]
+  uint64_t* a_empty = bars + 4;       // [4]
+  uint64_t* acc_full = bars + 8;      // [2]
+  uint64_t* acc_empty = bars + 10;    // [2]
+  uint64_t* w_full = bars + 12;       // [NS]
   uint64_t* w_empty = w_full + p.NS;  // [NS]
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);
     }
@@ -165,8 +168,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvPa
         const int b = tile / p.tiles_per_b;
         const int t0 = (tile - b * p.tiles_per_b) * 128;
         for (int cb = 0; cb < p.n_cb; ++cb) {
-          const uint32_t buf = qa & 1;
-          mbar_wait(&a_empty[buf], ((qa >> 1) & 1) ^ 1);
+          const uint32_t buf = qa % (uint32_t)p.NA;
+          mbar_wait(&a_empty[buf], ((qa / (uint32_t)p.NA) & 1) ^ 1);
           mbar_arrive_expect_tx(&a_full[buf], a_bytes);
           unsigned char* dst = sA + buf * a_bytes;
           for (int pl = 0; pl < 2; ++pl) {
@@ -214,8 +217,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvPa
         const uint32_t d_cross = d_main + (uint32_t)p.N;
         uint32_t accum = 0;
         for (int cb = 0; cb < p.n_cb; ++cb) {
-          const uint32_t buf = qa & 1;
-          mbar_wait(&a_full[buf], (qa >> 1) & 1);
+          const uint32_t buf = qa % (uint32_t)p.NA;
+          mbar_wait(&a_full[buf], (qa / (uint32_t)p.NA) & 1);
           const uint32_t a_hi = smem_u32(sA + buf * a_bytes);
           const uint32_t a_lo = a_hi + a_plane_bytes;
           for (int g = 0; g < p.SPC; ++g) {

@@ -163,7 +163,7 @@ static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
 struct TcLayer {
   bool ok = false;
   int C = 0, k = 0, dil = 1, pad = 0;
-  int KB = 0, n_cb = 0, JG = 0, SPC = 0, NS = 0, resident = 0, tmem_cols = 0, nbuf = 1;
+  int KB = 0, n_cb = 0, JG = 0, SPC = 0, NS = 0, resident = 0, tmem_cols = 0, nbuf = 1, NA = 2, ctas_per_sm = 1;
   size_t smem = 0;
   __half* w = nullptr;  // packed [cb][k][2][KB/8][N][8], device
   float inv_scale = 1.f;
@@ -186,22 +186,30 @@ static bool tc_plan(int C, int k, int dil, TcLayer* L) {
   L->SPC = (k + L->JG - 1) / L->JG;
   const size_t slot = (size_t)L->JG * w_tap;
   const int total_slots = L->n_cb * L->SPC;
-  const size_t misc = (size_t)((C + 1) & ~1) * 4 + 256;
-  if ((size_t)total_slots * slot <= 96 * 1024 && total_slots <= kTcMaxStages) {
-    L->resident = 1;
-    L->NS = total_slots;
-  } else {
-    L->resident = 0;
-    const size_t avail = kMaxDynSmem - 2 * a_bytes - misc - 8 * 20;
-    L->NS = (int)std::min<size_t>(8, avail / (slot + 16));
-    if (L->NS < 2) return false;
-  }
-  L->smem = 2 * a_bytes + (size_t)L->NS * slot + misc + (size_t)(8 + 2 * L->NS) * 8;
-  if (L->smem > kMaxDynSmem) return false;
+  const size_t misc = (size_t)((C + 1) & ~1) * 4 + 256 + 12 * 8;
   L->nbuf = (4 * C <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < L->nbuf * 2 * C) cols *= 2;
   L->tmem_cols = cols;
+  const int tmem_ctas = 512 / cols;
+  // Small layers are latency/HBM bound: keep the weights resident, deepen the activation pipeline and
+  // let several CTAs share an SM; large layers are MMA/L2 bound: one CTA per SM with a deep weight pipeline.
+  if ((size_t)total_slots * slot <= 96 * 1024 && total_slots <= kTcMaxStages) {
+    L->resident = 1;
+    L->NS = total_slots;
+    L->NA = (C <= 32) ? 4 : 2;
+  } else {
+    L->resident = 0;
+    L->NA = 2;
+    const size_t budget = (C <= 64 && tmem_ctas >= 2) ? kMaxDynSmem / 2 - 1024 : kMaxDynSmem;
+    const size_t fixed = (size_t)L->NA * a_bytes + misc;
+    if (budget <= fixed + 2 * (slot + 16)) return false;
+    L->NS = (int)std::min<size_t>(8, (budget - fixed) / (slot + 16));
+  }
+  L->smem = (size_t)L->NA * a_bytes + (size_t)L->NS * slot + misc + (size_t)(2 * L->NS) * 8;
+  if (L->smem > kMaxDynSmem) return false;
+  const int smem_ctas = (int)((228 * 1024) / (L->smem + 1024 + 128));
+  L->ctas_per_sm = std::max(1, std::min(std::min(smem_ctas, tmem_ctas), 6));
   L->ok = true;
   return true;
 }
@@ -255,11 +263,11 @@ static int launch_conv_tc(TcConvParams p, const TcLayer& L, cudaStream_t st) {
     attr_set = true;
   }
   p.k = L.k; p.dil = L.dil; p.pad = L.pad; p.KB = L.KB; p.n_cb = L.n_cb; p.JG = L.JG; p.SPC = L.SPC; p.NS = L.NS;
-  p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.nbuf = L.nbuf; p.w = L.w; p.w_inv_scale = L.inv_scale;
+  p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.nbuf = L.nbuf; p.NA = L.NA; p.w = L.w; p.w_inv_scale = L.inv_scale;
   p.Cin = L.C; p.N = L.C;
   p.tiles_per_b = p.Tr / 128;
   p.n_tiles = p.B * p.tiles_per_b;
-  const int grid = std::min(p.n_tiles, num_sms());
+  const int grid = std::min(p.n_tiles, num_sms() * L.ctas_per_sm);
   conv1d_tc_kernel<<<grid, kTcThreads, L.smem, st>>>(p);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
