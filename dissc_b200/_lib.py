@@ -40,7 +40,7 @@ EXPORTS = [
     "dissc_gen_create", "dissc_gen_destroy", "dissc_gen_hop", "dissc_gen_workspace_bytes", "dissc_gen_forward",
     "dissc_gen_forward_i16", "dissc_gen_forward_host", "dissc_gen_launches_per_forward", "dissc_gen_cost",
     "dissc_gen_profile", "dissc_conv1d_fused", "dissc_conv_transpose1d", "dissc_last_error", "dissc_version",
-    "dissc_gen_set_tensor_cores", "dissc_gen_tensor_core_stages", "dissc_conv1d_tc",
+    "dissc_gen_set_tensor_cores", "dissc_gen_tensor_core_stages", "dissc_conv1d_tc", "dissc_conv_transpose1d_tc",
 ]
 
 
@@ -78,8 +78,10 @@ def lib():
     L.dissc_gen_set_tensor_cores.argtypes = [c_void_p, c_int]
     L.dissc_gen_tensor_core_stages.argtypes = [c_void_p]
     L.dissc_conv1d_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
-                                  c_float, c_void_p]
+                                  c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                  c_float, c_float, c_void_p]
+    L.dissc_conv_transpose1d_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                            c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]
     _lib = L
     return L
 

@@ -1,0 +1,535 @@
+// Tensor-core implicit-GEMM convolution for the vocoder: tcgen05.mma (kind::f16) on split-fp16
+// operands so the result keeps fp32 accuracy.  One kernel serves
+//   * the dilated Conv1d of the ResBlocks (sr/models.py:36-40) with the residual / MRF epilogues,
+//   * conv_pre (:99) on the gathered embedding planes, and
+//   * the polyphase ConvTranspose1d upsamplers (:102): every output phase is a small dense conv
+//     over the INPUT frames, the phases are laid side by side along the GEMM N dimension.
+//
+//   D[r, n] = sum_j sum_ci A[r + j*dil - pad, ci] * W_j[ci, n]          r: 128 rows (time / frames) per tile
+//
+// Split precision: x = x_hi + x_lo (both fp16, weights pre-scaled by 2^s so w_lo stays normal) and
+//   x*w ~= x_hi*w_hi + (x_lo*w_hi + x_hi*w_lo)                          (error ~2^-22 relative)
+// N <= 128: TWO MMAs per 16-channel k-step:  A_hi x [W_hi | W_lo] -> [main | cross],  A_lo x W_hi -> cross
+//           (the weight planes sit side by side in shared memory so one N=2*NC MMA reads A once);
+// N == 256: three MMAs (hi*hi -> main, lo*hi -> cross, hi*lo -> cross), or all into one accumulator
+//           (single_acc) which frees half of TMEM for double buffering.
+// The cross terms get their own accumulator because the tensor core truncates the fp32 accumulator
+// after every MMA; the epilogue adds main + cross with a proper round-to-nearest.
+//
+// HBM layouts (channel-blocked, time-major):
+//   planes hi/lo : fp16 [B][C/8][Tp][8]   Tp = roundup(T,128) + 2*kTcHalo, kTcHalo zero rows either side
+//   f32b         : fp32 [B][C/8][Tr][8]   Tr = roundup(T,128)            (residual / MRF accumulator)
+// One (c8, row range) slab is contiguous, so an activation block is a handful of 1-D bulk TMA copies
+// and lands in shared memory as [c8][row][8] = the canonical no-swizzle K-major UMMA operand layout
+// (core matrix 8 rows x 16 B, SBO 128 B, LBO rows*16 B).  A tap shift of j*dil rows is +j*dil*16 B on
+// the descriptor start address: one resident block serves all taps.  The conv zero padding is the halo.
+// Weights are packed [chunk][cb][tap][c8][hi|lo][NC][8]: a pipeline stage is one contiguous bulk copy.
+//
+// CTA = 6 warps, persistent over work items (tile x N-chunk): warp 0 = producer (bulk TMA), warp 1 =
+// MMA issuer (one thread) + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> bias / residual /
+// MRF / leaky-relu -> fp16 split -> global).  TMEM accumulators ping-pong so the epilogue of item i
+// overlaps the MMAs of item i+1.  All slot / phase bookkeeping is incremental (no div/mod in the loops).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace dissc {
+
+constexpr int kTcThreads = 192;
+constexpr int kTcHalo = 32;       // zero rows either side of every plane row-slab (>= max conv padding 25)
+constexpr int kTcMaxStages = 64;  // barrier slots for the weight pipeline (resident mode: one per stage)
+
+struct TcParams {
+  const __half* a_hi;  // planes [B][Cin8][Tp_in][8]
+  const __half* a_lo;
+  const __half* w;     // packed [chunk][cb][tap][KB/8][2][NC][8]
+  const float* bias;   // [Cout]
+  float w_inv_scale;   // 2^-s
+  const float* res;     // f32b [B][Cout/8][Tr][8] or null
+  const float* acc_in;  // f32b or null
+  float* out_f32b;      // f32b or null (raw value)
+  __half* out_hi;       // planes [B][Cout/8][Tp][8] (leaky-relu(plane_slope) applied iff plane_act) or null
+  __half* out_lo;
+  float* out_plain;     // (B, Cout, T) fp32 (leaky-relu(plain_slope) iff plain_act) or null
+  const int* lengths;
+  int len_mul;          // valid OUTPUT rows of utterance b = lengths[b] * len_mul
+  int B, Cin8, Cout, T, Tp, Tr, Tp_in;
+  int k, dil, pad;      // taps, dilation, left padding in rows (transposed conv: k = taps per phase, pad = k-1)
+  int KB;               // channels per activation block (16 or 32)
+  int n_cb;             // Cin_padded / KB
+  int JG;               // taps per weight stage
+  int SPC;              // weight stages per channel block = ceil(k / JG)
+  int NS;               // weight slots in shared memory
+  int resident;         // 1: NS == n_cb*SPC and n_chunks == 1, weights loaded once per CTA
+  int n_chunks;         // N chunks of NC columns
+  int tiles_per_b, n_items;
+  int tmem_cols;        // allocation (power of two)
+  int acc_cols;         // TMEM columns per accumulator buffer (2*NC, or NC with single_acc)
+  int NA;               // activation-block buffers in shared memory (2..4)
+  int nbuf;             // TMEM accumulator buffers (1 or 2)
+  int single_acc;       // NC == 256 only: all three MMAs into one accumulator
+  int up;               // 0: conv.  u > 0: transposed conv with stride u; tile rows are input frames,
+  int up_P;             //   a chunk holds up_P phases x Cout channels, output row = frame*u + phase - up_pad
+  int up_pad;
+  float div;
+  int plane_act, plain_act;
+  float plane_slope, plain_slope;
+};
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------
+// K-major, no swizzle: start address >> 4 | LBO >> 4 (K-chunk stride) << 16 ; high word: SBO (=128 B, stride between
+// 8-row groups) >> 4 | descriptor version 1 << 14.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+constexpr uint32_t kUmmaDescHi = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo) { return ((uint64_t)kUmmaDescHi << 32) | lo; }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void split_store8(__half* hi_dst, __half* lo_dst, const float v[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float c0 = fminf(fmaxf(v[2 * i], -65504.f), 65504.f);
+    const float c1 = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+    const __half2 hh = __floats2half2_rn(c0, c1);
+    const float2 back = __half22float2(hh);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = pack_half2(c0 - back.x, c1 - back.y);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC == 64) ? 2 : 1)) conv_tc_kernel(const TcParams p) {
+  constexpr bool kTwoMma = (NC <= 128);
+  constexpr int G = NC / 8;            // 8-channel groups per chunk
+  constexpr int EB = 2;                // groups per epilogue batch
+  constexpr int NB = G / EB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int R = 128 + (p.k - 1) * p.dil;                          // activation rows a tile needs
+  const uint32_t lbo_a = (uint32_t)R * 16;                        // bytes between 8-channel chunks of A
+  const uint32_t a_plane_bytes = (uint32_t)(p.KB / 8) * lbo_a;    // one plane of one block
+  const uint32_t a_bytes = 2 * a_plane_bytes;
+  constexpr uint32_t lbo_b = 2u * NC * 16;                        // [c8][hi|lo][NC][8]
+  const uint32_t w_tap_bytes = (uint32_t)(p.KB / 8) * lbo_b;
+  const uint32_t w_slot_bytes = (uint32_t)p.JG * w_tap_bytes;
+  unsigned char* sA = smem_raw;
+  unsigned char* sW = sA + (size_t)p.NA * a_bytes;
+  float* s_bias = reinterpret_cast<float*>(sW + (size_t)p.NS * w_slot_bytes);  // [n_chunks*NC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + ((p.n_chunks * NC + 1) & ~1));
+  uint64_t* a_full = bars;            // [4]
+  uint64_t* a_empty = bars + 4;       // [4]
+  uint64_t* acc_full = bars + 8;      // [2]
+  uint64_t* acc_empty = bars + 10;    // [2]
+  uint64_t* w_full = bars + 12;       // [NS]
+  uint64_t* w_empty = w_full + p.NS;  // [NS]
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    for (int i = 0; i < p.NS; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < p.n_chunks * NC; i += kTcThreads) {
+    const int co = p.up ? (i % p.Cout) : i;
+    s_bias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer: bulk TMA =====================
+    if (lane == 0) {
+      uint32_t abuf = 0, aph = 0, ws = 0, wph = 0;
+      bool first = true;
+      const int kb8 = p.KB / 8;
+      int chunk = blockIdx.x % p.n_chunks, tile = blockIdx.x / p.n_chunks;
+      const int dchunk = gridDim.x % p.n_chunks, dtile = gridDim.x / p.n_chunks;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int b = tile / p.tiles_per_b;
+        const int r0 = (tile - b * p.tiles_per_b) * 128;
+        const __half* hi0 = p.a_hi + (((size_t)b * p.Cin8) * p.Tp_in + kTcHalo + r0 - p.pad) * 8;
+        const __half* lo0 = p.a_lo + (((size_t)b * p.Cin8) * p.Tp_in + kTcHalo + r0 - p.pad) * 8;
+        const unsigned char* wchunk = reinterpret_cast<const unsigned char*>(p.w) +
+                                      (size_t)chunk * p.n_cb * p.k * w_tap_bytes;
+        for (int cb = 0; cb < p.n_cb; ++cb) {
+          mbar_wait(&a_empty[abuf], aph ^ 1);
+          mbar_arrive_expect_tx(&a_full[abuf], a_bytes);
+          unsigned char* dst = sA + abuf * a_bytes;
+          for (int c8 = 0; c8 < kb8; ++c8) {
+            const size_t off = (size_t)(cb * kb8 + c8) * p.Tp_in * 8;
+            tma_load_1d(dst + (size_t)c8 * lbo_a, hi0 + off, lbo_a, &a_full[abuf]);
+            tma_load_1d(dst + a_plane_bytes + (size_t)c8 * lbo_a, lo0 + off, lbo_a, &a_full[abuf]);
+          }
+          if (++abuf == (uint32_t)p.NA) { abuf = 0; aph ^= 1; }
+          if (!p.resident || first) {
+            int j0 = 0;
+            for (int g = 0; g < p.SPC; ++g, j0 += p.JG) {
+              const int nt = min(p.JG, p.k - j0);
+              const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
+              if (!p.resident) mbar_wait(&w_empty[slot], wph ^ 1);
+              mbar_arrive_expect_tx(&w_full[slot], (uint32_t)nt * w_tap_bytes);
+              tma_load_1d(sW + (size_t)slot * w_slot_bytes, wchunk + ((size_t)cb * p.k + j0) * w_tap_bytes,
+                          (uint32_t)nt * w_tap_bytes, &w_full[slot]);
+              if (++ws == (uint32_t)p.NS) { ws = 0; wph ^= 1; }
+            }
+          }
+        }
+        first = false;
+        chunk += dchunk; tile += dtile;
+        if (chunk >= p.n_chunks) { chunk -= p.n_chunks; ++tile; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+      constexpr uint32_t idesc_n = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * NC) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t sA0 = smem_u32(sA), sW0 = smem_u32(sW);
+      const int KS = p.KB / 16;
+      const uint32_t a_kstep = (2 * lbo_a) >> 4, b_kstep = (2 * lbo_b) >> 4;  // descriptor units (16 B)
+      const uint32_t a_lo_off = a_plane_bytes >> 4;
+      uint32_t abuf = 0, aph = 0, ws = 0, wph = 0, ab = 0, accph = 0;
+      bool first = true;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        mbar_wait(&acc_empty[ab], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + ab * (uint32_t)p.acc_cols;
+        const uint32_t d_cross = p.single_acc ? d_main : d_main + NC;
+        uint32_t accum = 0;
+        for (int cb = 0; cb < p.n_cb; ++cb) {
+          mbar_wait(&a_full[abuf], aph);
+          const uint32_t a_desc0 = umma_desc_lo(sA0 + abuf * a_bytes, lbo_a);
+          int j0 = 0;
+          for (int g = 0; g < p.SPC; ++g, j0 += p.JG) {
+            const int nt = min(p.JG, p.k - j0);
+            const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
+            if (!p.resident)
+              mbar_wait(&w_full[slot], wph);
+            else if (first)
+              mbar_wait(&w_full[slot], 0);
+            tc_fence_after();
+            uint32_t w_desc = umma_desc_lo(sW0 + slot * w_slot_bytes, lbo_b);
+            uint32_t a_desc = a_desc0 + (uint32_t)(j0 * p.dil);
+            for (int jj = 0; jj < nt; ++jj, a_desc += (uint32_t)p.dil, w_desc += (w_tap_bytes >> 4)) {
+              uint32_t ad = a_desc, wd = w_desc;
+              for (int ks = 0; ks < KS; ++ks, ad += a_kstep, wd += b_kstep) {
+                if constexpr (kTwoMma) {
+                  umma_f16(d_main, umma_desc(ad), umma_desc(wd), idesc_2n, accum);            // [main | cross]
+                  umma_f16(d_cross, umma_desc(ad + a_lo_off), umma_desc(wd), idesc_n, 1);     // cross += lo*hi
+                } else {
+                  umma_f16(d_main, umma_desc(ad), umma_desc(wd), idesc_n, accum);
+                  umma_f16(d_cross, umma_desc(ad + a_lo_off), umma_desc(wd), idesc_n, p.single_acc ? 1u : accum);
+                  umma_f16(d_cross, umma_desc(ad), umma_desc(wd + NC), idesc_n, 1);
+                }
+                accum = 1;
+              }
+            }
+            if (!p.resident) umma_commit(&w_empty[slot]);
+            if (++ws == (uint32_t)p.NS) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(&a_empty[abuf]);
+          if (++abuf == (uint32_t)p.NA) { abuf = 0; aph ^= 1; }
+        }
+        umma_commit(&acc_full[ab]);
+        if (++ab == (uint32_t)p.nbuf) { ab = 0; accph ^= 1; }
+        first = false;
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int cout8 = p.Cout / 8;
+    uint32_t ab = 0, accph = 0;
+    int chunk = blockIdx.x % p.n_chunks, tile = blockIdx.x / p.n_chunks;
+    const int dchunk = gridDim.x % p.n_chunks, dtile = gridDim.x / p.n_chunks;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int b = tile / p.tiles_per_b;
+      const int r = (tile - b * p.tiles_per_b) * 128 + row;
+      const int Tvalid = p.lengths ? min(p.T, p.lengths[b] * p.len_mul) : p.T;
+      // residual of the first batch: issued before the accumulator wait so its latency hides behind the MMAs
+      float4 rq[EB * 2];
+      const bool conv_valid = (!p.up) && r < Tvalid;
+      const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * G) * p.Tr + r) * 8;  // conv mode only
+      const size_t fstride = (size_t)p.Tr * 8;
+      if (p.res && conv_valid) {
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+          rq[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + e * fstride);
+          rq[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + e * fstride + 4);
+        }
+      }
+      mbar_wait(&acc_full[ab], accph);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * (uint32_t)p.acc_cols;
+#pragma unroll 1
+      for (int bi = 0; bi < NB; ++bi) {
+        float m[EB][8], x[EB][8];
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+          tmem_ld8(taddr0 + (bi * EB + e) * 8, m[e]);
+          if (!p.single_acc) tmem_ld8(taddr0 + NC + (bi * EB + e) * 8, x[e]);
+        }
+        float4 rn[EB * 2];
+        if (NB > 1 && bi + 1 < NB && p.res && conv_valid) {
+          // prefetch the next batch's residual while this one is processed
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
+            rn[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + ((bi + 1) * EB + e) * fstride);
+            rn[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + ((bi + 1) * EB + e) * fstride + 4);
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+          const int g8 = bi * EB + e;      // 8-column group inside the chunk
+          const int n0 = chunk * NC + g8 * 8;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float s = p.single_acc ? m[e][i] : (m[e][i] + x[e][i]);
+            v[i] = s * p.w_inv_scale + s_bias[n0 + i];
+          }
+          int t, c8o;
+          bool inb, valid;
+          if (p.up) {
+            const int phase = n0 / p.Cout;
+            c8o = (n0 - phase * p.Cout) >> 3;
+            t = r * p.up + phase - p.up_pad;
+            inb = t >= 0 && t < p.T;
+            valid = inb && t < Tvalid;
+          } else {
+            c8o = n0 >> 3;
+            t = r;
+            inb = true;
+            valid = conv_valid;
+          }
+          if (c8o >= cout8) continue;  // padded output columns
+          const size_t fidx = (((size_t)b * cout8 + c8o) * p.Tr + t) * 8;
+          if (valid) {
+            if (p.res) {
+              v[0] += rq[2 * e].x; v[1] += rq[2 * e].y; v[2] += rq[2 * e].z; v[3] += rq[2 * e].w;
+              v[4] += rq[2 * e + 1].x; v[5] += rq[2 * e + 1].y; v[6] += rq[2 * e + 1].z; v[7] += rq[2 * e + 1].w;
+            }
+            if (p.acc_in) {
+              const float4 r0 = *reinterpret_cast<const float4*>(p.acc_in + fidx);
+              const float4 r1 = *reinterpret_cast<const float4*>(p.acc_in + fidx + 4);
+              v[0] = r0.x + v[0]; v[1] = r0.y + v[1]; v[2] = r0.z + v[2]; v[3] = r0.w + v[3];
+              v[4] = r1.x + v[4]; v[5] = r1.y + v[5]; v[6] = r1.z + v[6]; v[7] = r1.w + v[7];
+            }
+            if (p.div != 0.f) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = v[i] / p.div;
+            }
+            if (p.out_f32b) {
+              *reinterpret_cast<float4*>(p.out_f32b + fidx) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(p.out_f32b + fidx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            if (p.out_plain) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                p.out_plain[((size_t)b * p.Cout + c8o * 8 + i) * p.T + t] = p.plain_act ? leaky(v[i], p.plain_slope) : v[i];
+            }
+          }
+          if (p.out_hi && inb) {
+            // rows >= valid length are written as zeros: they are the next conv's zero padding
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = valid ? (p.plane_act ? leaky(v[i], p.plane_slope) : v[i]) : 0.f;
+            const size_t pidx = (((size_t)b * cout8 + c8o) * p.Tp + kTcHalo + t) * 8;
+            split_store8(p.out_hi + pidx, p.out_lo + pidx, a);
+          }
+        }
+        if (NB > 1) {
+#pragma unroll
+          for (int e = 0; e < EB * 2; ++e) rq[e] = rn[e];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      if (++ab == (uint32_t)p.nbuf) { ab = 0; accph ^= 1; }
+      chunk += dchunk; tile += dtile;
+      if (chunk >= p.n_chunks) { chunk -= p.n_chunks; ++tile; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+// Zero rows [0,HP) and [HP+T, Tp) of every (b, c8) slab of a plane pair: the conv zero padding
+// (left halo, the round-up rows [T,Tr) and the right halo).
+__global__ void tc_zero_halos_kernel(__half* hi, __half* lo, int slabs, int Tp, int T) {
+  const int per = kTcHalo + (Tp - kTcHalo - T);  // rows per slab to clear
+  const long long total = (long long)slabs * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i / per);
+    int r = (int)(i - (long long)s * per);
+    r = r < kTcHalo ? r : (T + r);  // second range starts at row HP+T
+    const size_t off = ((size_t)s * Tp + r) * 8;
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// Fused gather/concat of CodeGenerator.forward (sr/models.py:189,:206-215) straight into the split planes that
+// conv_pre consumes: channels [0,E) = dict[code[b,t]], [E] = f0[b,t], then spkr_emb[spkr[b]] repeated over time;
+// channels >= Cin and every row outside [0, valid length) are written as zeros (halos included).
+struct EmbedParams {
+  const long long* code;  // (B, T)
+  const float* f0;        // (B, T) or null
+  const long long* spkr;  // (B) or null
+  const float* dict_w;    // (num_embeddings, E)
+  const float* spkr_w;    // (rows, E)
+  const int* lengths;
+  int E, f0_ch, spk_base, Cin;  // f0_ch / spk_base = -1 if absent
+  int B, C8, T, Tp;
+  __half* hi;
+  __half* lo;
+};
+__global__ void tc_embed_planes_kernel(const EmbedParams p) {
+  const long long total = (long long)p.B * p.C8 * p.Tp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i % p.Tp);
+    const long long s = i / p.Tp;
+    const int c8 = (int)(s % p.C8), b = (int)(s / p.C8);
+    const int t = row - kTcHalo;
+    const int Tvalid = p.lengths ? min(p.T, p.lengths[b]) : p.T;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ci = c8 * 8 + e;
+      float x = 0.f;
+      if (t >= 0 && t < Tvalid && ci < p.Cin) {
+        if (ci < p.E) {
+          x = __ldg(p.dict_w + (size_t)p.code[(size_t)b * p.T + t] * p.E + ci);
+        } else if (ci == p.f0_ch) {
+          x = __ldg(p.f0 + (size_t)b * p.T + t);
+        } else if (p.spk_base >= 0 && ci >= p.spk_base) {
+          x = __ldg(p.spkr_w + (size_t)p.spkr[b] * p.E + (ci - p.spk_base));
+        }
+      }
+      v[e] = x;
+    }
+    split_store8(p.hi + (size_t)i * 8, p.lo + (size_t)i * 8, v);
+  }
+}
+
+// plain (B,C,T) fp32 -> split planes [B][C8][Tp][8] (+ optional leaky-relu); rows >= valid length and channels >= C
+// are zero.  Layer-test helper (the model writes planes straight from the producing kernel's epilogue).
+__global__ void tc_pack_planes_kernel(const float* in, __half* hi, __half* lo, const int* lengths, int len_mul, int B, int C,
+                                      int C8, int T, int Tp, int act, float slope) {
+  const long long total = (long long)B * C8 * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const long long s = i / T;  // slab = b*C8 + c8
+    const int b = (int)(s / C8), c8 = (int)(s % C8);
+    const int Tvalid = lengths ? min(T, lengths[b] * len_mul) : T;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c8 * 8 + e;
+      float x = (t < Tvalid && c < C) ? in[((size_t)b * C + c) * T + t] : 0.f;
+      v[e] = act ? leaky(x, slope) : x;
+    }
+    const size_t off = ((size_t)s * Tp + kTcHalo + t) * 8;
+    split_store8(hi + off, lo + off, v);
+  }
+}
+
+// plain (B,C,T) fp32 <-> blocked f32b [B][C/8][Tr][8] (layer-test helpers)
+__global__ void tc_plain_to_f32b_kernel(const float* in, float* out, int B, int C, int T, int Tr) {
+  const long long total = (long long)B * C * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const long long bc = i / T;
+    const int c = (int)(bc % C), b = (int)(bc / C);
+    out[(((size_t)b * (C / 8) + c / 8) * Tr + t) * 8 + (c & 7)] = in[i];
+  }
+}
+__global__ void tc_f32b_to_plain_kernel(const float* in, float* out, int B, int C, int T, int Tr) {
+  const long long total = (long long)B * C * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const long long bc = i / T;
+    const int c = (int)(bc % C), b = (int)(bc / C);
+    out[i] = in[(((size_t)b * (C / 8) + c / 8) * Tr + t) * 8 + (c & 7)];
+  }
+}
+// planes -> plain fp32 (hi + lo), for tests
+__global__ void tc_planes_to_plain_kernel(const __half* hi, const __half* lo, float* out, int B, int C, int T, int Tp) {
+  const long long total = (long long)B * C * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const long long bc = i / T;
+    const int c = (int)(bc % C), b = (int)(bc / C);
+    const size_t off = (((size_t)b * (C / 8) + c / 8) * Tp + kTcHalo + t) * 8 + (c & 7);
+    out[i] = __half2float(hi[off]) + __half2float(lo[off]);
+  }
+}
+
+}  // namespace dissc

@@ -19,7 +19,7 @@
 
 #include "common.cuh"
 #include "conv1d.cuh"
-#include "conv1d_tc.cuh"
+#include "conv_tc.cuh"
 #include "conv_post.cuh"
 #include "convt1d.cuh"
 
@@ -162,62 +162,89 @@ static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
 // ------------------------------------------------------------------------
 struct TcLayer {
   bool ok = false;
-  int C = 0, k = 0, dil = 1, pad = 0;
-  int KB = 0, n_cb = 0, JG = 0, SPC = 0, NS = 0, resident = 0, tmem_cols = 0, nbuf = 1, NA = 2, ctas_per_sm = 1;
+  int Cin = 0, Cin_pad = 0, Cout = 0, NC = 0, n_chunks = 1;
+  int k = 0, dil = 1, pad = 0;       // taps / dilation / left padding of the implicit GEMM
+  int up = 0, up_P = 0, up_pad = 0;  // transposed conv: stride, phases per chunk, padding
+  int KB = 0, n_cb = 0, JG = 0, SPC = 0, NS = 0, resident = 0, tmem_cols = 0, acc_cols = 0, nbuf = 1, NA = 2;
+  int single_acc = 0, ctas_per_sm = 1;
   size_t smem = 0;
-  __half* w = nullptr;  // packed [cb][k][2][KB/8][N][8], device
+  __half* w = nullptr;  // packed [chunk][cb][tap][KB/8][hi|lo][NC][8], device
   float inv_scale = 1.f;
 };
 
-constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // 227 KB per CTA minus the kernel's static shared memory
+constexpr size_t kSmemPerSm = 227 * 1024;
+static int g_single_acc256 = -1;  // NC == 256: one accumulator (double-buffered TMEM) instead of main+cross
 
-static bool tc_plan(int C, int k, int dil, TcLayer* L) {
+// Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
+static bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L) {
   L->ok = false;
-  if (C % 16 != 0 || C < 16 || C > 256) return false;
-  const int pad = (k * dil - dil) / 2;
-  if (pad > kTcHalo || k < 1) return false;
-  L->C = C; L->k = k; L->dil = dil; L->pad = pad;
-  L->KB = C >= 32 ? 32 : 16;
-  L->n_cb = C / L->KB;
-  const int R = 128 + (k - 1) * dil;
+  if (Cin < 1 || taps < 1 || pad > kTcHalo || pad < 0) return false;
+  if ((taps - 1) * dil - pad > kTcHalo) return false;  // right halo
+  int NC;
+  if (ncols <= 256) {
+    if (ncols != 16 && ncols != 32 && ncols != 64 && ncols != 128 && ncols != 256) return false;
+    NC = ncols;
+  } else {
+    if (ncols % 256) return false;
+    NC = 256;
+  }
+  if (g_single_acc256 < 0) {
+    const char* e = getenv("DISSC_TC_SINGLE_ACC");
+    g_single_acc256 = e ? (atoi(e) != 0) : 0;
+  }
+  L->Cin = Cin; L->Cin_pad = (Cin + 15) / 16 * 16; L->NC = NC; L->n_chunks = ncols / NC;
+  L->k = taps; L->dil = dil; L->pad = pad;
+  L->KB = (L->Cin_pad % 32 == 0) ? 32 : 16;
+  L->n_cb = L->Cin_pad / L->KB;
+  L->single_acc = (NC == 256) ? g_single_acc256 : 0;
+  L->acc_cols = L->single_acc ? NC : 2 * NC;
+  L->nbuf = (2 * L->acc_cols <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < L->nbuf * L->acc_cols) cols *= 2;
+  L->tmem_cols = cols;
+  const int R = 128 + (taps - 1) * dil;
   const size_t a_bytes = (size_t)4 * L->KB * R;
-  const size_t w_tap = (size_t)4 * L->KB * C;
-  L->JG = (int)std::min<size_t>(std::max<size_t>(32768 / w_tap, 1), k);
-  L->SPC = (k + L->JG - 1) / L->JG;
+  const size_t w_tap = (size_t)4 * L->KB * NC;
+  L->SPC = (int)std::max<size_t>(1, ((size_t)taps * w_tap + 32767) / 32768);
+  L->JG = (taps + L->SPC - 1) / L->SPC;
+  L->SPC = (taps + L->JG - 1) / L->JG;
   const size_t slot = (size_t)L->JG * w_tap;
   const int total_slots = L->n_cb * L->SPC;
-  const size_t misc = (size_t)((C + 1) & ~1) * 4 + 256 + 12 * 8;
-  L->nbuf = (4 * C <= 512) ? 2 : 1;
-  int cols = 32;
-  while (cols < L->nbuf * 2 * C) cols *= 2;
-  L->tmem_cols = cols;
-  const int tmem_ctas = 512 / cols;
-  // Small layers are latency/HBM bound: keep the weights resident, deepen the activation pipeline and
-  // let several CTAs share an SM; large layers are MMA/L2 bound: one CTA per SM with a deep weight pipeline.
-  if ((size_t)total_slots * slot <= 96 * 1024 && total_slots <= kTcMaxStages) {
-    L->resident = 1;
-    L->NS = total_slots;
-    L->NA = (C <= 32) ? 4 : 2;
-  } else {
-    L->resident = 0;
-    L->NA = 2;
-    const size_t budget = (C <= 64 && tmem_ctas >= 2) ? kMaxDynSmem / 2 - 1024 : kMaxDynSmem;
-    const size_t fixed = (size_t)L->NA * a_bytes + misc;
-    if (budget <= fixed + 2 * (slot + 16)) return false;
-    L->NS = (int)std::min<size_t>(8, (budget - fixed) / (slot + 16));
+  int cap = NC <= 32 ? 3 : (NC == 64 ? 2 : 1);  // matches __launch_bounds__ of conv_tc_kernel<NC>
+  cap = std::min(cap, 512 / cols);
+  for (int ctas = cap; ctas >= 1; --ctas) {
+    const size_t budget = kSmemPerSm / ctas - 1536;  // static shared + alignment + per-CTA reservation
+    auto misc = [&](int ns) { return (size_t)((L->n_chunks * NC + 1) & ~1) * 4 + (size_t)(12 + 2 * ns) * 8 + 128; };
+    if (L->n_chunks == 1 && total_slots <= kTcMaxStages) {
+      for (int na = 4; na >= 2; --na) {
+        const size_t need = (size_t)na * a_bytes + (size_t)total_slots * slot + misc(total_slots);
+        if (need <= budget) {
+          L->resident = 1; L->NS = total_slots; L->NA = na; L->smem = need; L->ctas_per_sm = ctas; L->ok = true;
+          return true;
+        }
+      }
+    }
+    const size_t fixed = 2 * a_bytes + misc(8);
+    if (budget > fixed + 2 * slot) {
+      L->resident = 0; L->NA = 2;
+      L->NS = (int)std::min<size_t>(8, (budget - fixed) / slot);
+      L->smem = 2 * a_bytes + (size_t)L->NS * slot + misc(L->NS);
+      L->ctas_per_sm = ctas; L->ok = true;
+      return true;
+    }
   }
-  L->smem = (size_t)L->NA * a_bytes + (size_t)L->NS * slot + misc + (size_t)(2 * L->NS) * 8;
-  if (L->smem > kMaxDynSmem) return false;
-  const int smem_ctas = (int)((228 * 1024) / (L->smem + 1024 + 128));
-  L->ctas_per_sm = std::max(1, std::min(std::min(smem_ctas, tmem_ctas), 6));
-  L->ok = true;
-  return true;
+  return false;
 }
 
-// w: (Cout=N, Cin, k) fp32 -> fp16 hi/lo planes of w*2^s, layout [cb][k][2][KB/8][N][8]
-static std::vector<__half> pack_weights_tc(const float* w, int C, int k, int KB, float* inv_scale) {
+// Generic packer: wval(n, ci, tap) is the GEMM weight of column n (0 <= n < n_chunks*NC).  Output fp16 hi/lo planes of
+// w*2^s, layout [chunk][cb][tap][KB/8][hi|lo][NC][8].
+template <typename F>
+static std::vector<__half> pack_weights_tc(const TcLayer& L, F wval, float* inv_scale) {
+  const int ncols = L.n_chunks * L.NC;
   float mx = 0.f;
-  for (size_t i = 0; i < (size_t)C * C * k; ++i) mx = std::max(mx, std::fabs(w[i]));
+  for (int n = 0; n < ncols; ++n)
+    for (int ci = 0; ci < L.Cin; ++ci)
+      for (int j = 0; j < L.k; ++j) mx = std::max(mx, std::fabs(wval(n, ci, j)));
   int s = 0;
   if (mx > 0.f) {
     int e;
@@ -227,23 +254,46 @@ static std::vector<__half> pack_weights_tc(const float* w, int C, int k, int KB,
   }
   const float scale = std::ldexp(1.f, s);
   *inv_scale = std::ldexp(1.f, -s);
-  const int n_cb = C / KB;
-  std::vector<__half> out((size_t)n_cb * k * 2 * (KB / 8) * C * 8);
-  for (int cb = 0; cb < n_cb; ++cb)
-    for (int j = 0; j < k; ++j)
-      for (int c8 = 0; c8 < KB / 8; ++c8)
-        for (int n = 0; n < C; ++n)
-          for (int e = 0; e < 8; ++e) {
-            const int ci = cb * KB + c8 * 8 + e;
-            const float v = w[((size_t)n * C + ci) * k + j] * scale;
-            const __half h = __float2half_rn(v);
-            const __half l = __float2half_rn(v - __half2float(h));
-            const size_t base = ((size_t)cb * k + j) * 2;
-            out[(((base + 0) * (KB / 8) + c8) * C + n) * 8 + e] = h;
-            out[(((base + 1) * (KB / 8) + c8) * C + n) * 8 + e] = l;
-          }
+  const int kb8 = L.KB / 8;
+  std::vector<__half> out((size_t)L.n_chunks * L.n_cb * L.k * kb8 * 2 * L.NC * 8);
+  size_t o = 0;
+  for (int ch = 0; ch < L.n_chunks; ++ch)
+    for (int cb = 0; cb < L.n_cb; ++cb)
+      for (int j = 0; j < L.k; ++j)
+        for (int c8 = 0; c8 < kb8; ++c8) {
+          __half* hi = &out[o];
+          __half* lo = hi + (size_t)L.NC * 8;
+          o += (size_t)2 * L.NC * 8;
+          for (int n = 0; n < L.NC; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = cb * L.KB + c8 * 8 + e;
+              const float v = (ci < L.Cin ? wval(ch * L.NC + n, ci, j) : 0.f) * scale;
+              const __half h = __float2half_rn(v);
+              hi[n * 8 + e] = h;
+              lo[n * 8 + e] = __float2half_rn(v - __half2float(h));
+            }
+        }
   return out;
 }
+
+static bool tc_plan_conv(int Cin, int Cout, int k, int dil, TcLayer* L) {
+  if (Cout % 8) return false;
+  if (!tc_plan(Cin, Cout, k, dil, (k * dil - dil) / 2, L)) return false;
+  L->Cout = Cout;
+  return true;
+}
+// Polyphase transposed conv (Cin, Cout, k) stride u, padding (k-u)/2: M = ceil(k/u) taps per phase; GEMM column
+// n = phase*Cout + co; tap j' reads input frame q - (M-1) + j' and carries W[:, co, phase + (M-1-j')*u].
+static bool tc_plan_convt(int Cin, int Cout, int k, int u, TcLayer* L) {
+  if (Cout % 8 || Cout > 256 || u < 1) return false;
+  const int M = (k + u - 1) / u;
+  if (!tc_plan(Cin, u * Cout, M, 1, M - 1, L)) return false;
+  if (L->NC % Cout) { L->ok = false; return false; }
+  L->Cout = Cout; L->up = u; L->up_P = L->NC / Cout; L->up_pad = (k - u) / 2;
+  return true;
+}
+
+static int tc_upload(dissc_gen* g, const std::vector<__half>& packed, __half** out);
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -256,21 +306,38 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static int launch_conv_tc(TcConvParams p, const TcLayer& L, cudaStream_t st) {
+template <int NC>
+static int launch_conv_tc_nc(const TcParams& p, const TcLayer& L, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DISSC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    DISSC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSmemPerSm - 1024)));
     attr_set = true;
   }
-  p.k = L.k; p.dil = L.dil; p.pad = L.pad; p.KB = L.KB; p.n_cb = L.n_cb; p.JG = L.JG; p.SPC = L.SPC; p.NS = L.NS;
-  p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.nbuf = L.nbuf; p.NA = L.NA; p.w = L.w; p.w_inv_scale = L.inv_scale;
-  p.Cin = L.C; p.N = L.C;
-  p.tiles_per_b = p.Tr / 128;
-  p.n_tiles = p.B * p.tiles_per_b;
-  const int grid = std::min(p.n_tiles, num_sms() * L.ctas_per_sm);
-  conv1d_tc_kernel<<<grid, kTcThreads, L.smem, st>>>(p);
+  conv_tc_kernel<NC><<<grid, kTcThreads, L.smem, st>>>(p);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
+}
+
+// p carries the tensors, B, T (output rows), Tr, Tp, Tp_in, lengths and the epilogue switches; `rows` is the number of
+// GEMM rows per utterance (output time steps for a conv, input frames for a transposed conv).
+static int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
+  p.k = L.k; p.dil = L.dil; p.pad = L.pad; p.KB = L.KB; p.n_cb = L.n_cb; p.JG = L.JG; p.SPC = L.SPC; p.NS = L.NS;
+  p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.acc_cols = L.acc_cols; p.nbuf = L.nbuf; p.NA = L.NA;
+  p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale;
+  p.Cin8 = L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
+  p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
+  p.tiles_per_b = (rows + 127) / 128;
+  p.n_items = p.B * p.tiles_per_b * L.n_chunks;
+  const int grid = std::min(p.n_items, num_sms() * L.ctas_per_sm);
+  switch (L.NC) {
+    case 16: return launch_conv_tc_nc<16>(p, L, grid, st);
+    case 32: return launch_conv_tc_nc<32>(p, L, grid, st);
+    case 64: return launch_conv_tc_nc<64>(p, L, grid, st);
+    case 128: return launch_conv_tc_nc<128>(p, L, grid, st);
+    case 256: return launch_conv_tc_nc<256>(p, L, grid, st);
+  }
+  return set_err(DISSC_EINVAL, "bad tensor-core chunk width %d", L.NC);
 }
 
 static int launch_zero_halos(__half* hi, __half* lo, int slabs, int Tp, int T, cudaStream_t st) {
@@ -321,6 +388,8 @@ struct dissc_gen {
   // tensor-core twins of rb[][][][] and per-stage eligibility
   TcLayer rb_tc[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS][2];
   bool stage_tc[DISSC_MAX_STAGES] = {};
+  TcLayer pre_tc, ups_tc[DISSC_MAX_STAGES];  // conv_pre / upsamplers on the tensor cores
+  bool tc_all = false;                        // every layer but conv_post has a tcgen05 plan: planes flow end to end
   int use_tc = 1;
   float* dict_w = nullptr;
   float* spkr_w = nullptr;
@@ -369,16 +438,35 @@ static int make_conv(dissc_gen* g, const WeightMap& wm, const std::string& prefi
   return dev_upload(g, b->data, Cout, &L->bias);
 }
 
-static int make_conv_tc(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int C, int k, int dil, TcLayer* L) {
-  if (!tc_plan(C, k, dil, L)) return DISSC_OK;  // not eligible: the fp32 CUDA-core kernel handles it
-  const dissc_tensor* w = wm.get(prefix + ".weight");
-  auto packed = pack_weights_tc(w->data, C, k, L->KB, &L->inv_scale);
+static int tc_upload(dissc_gen* g, const std::vector<__half>& packed, __half** out) {
   __half* d = nullptr;
   DISSC_CUDA(cudaMalloc(&d, packed.size() * sizeof(__half)));
   g->allocs.push_back(d);
   DISSC_CUDA(cudaMemcpy(d, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  L->w = d;
+  *out = d;
   return DISSC_OK;
+}
+
+static int make_conv_tc(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int Cin, int Cout, int k, int dil,
+                        TcLayer* L) {
+  if (!tc_plan_conv(Cin, Cout, k, dil, L)) return DISSC_OK;  // not eligible: the fp32 CUDA-core kernel handles it
+  const float* w = wm.get(prefix + ".weight")->data;         // (Cout, Cin, k)
+  auto packed = pack_weights_tc(*L, [=](int n, int ci, int j) { return w[((size_t)n * Cin + ci) * k + j]; },
+                                &L->inv_scale);
+  return tc_upload(g, packed, &L->w);
+}
+
+static int make_convt_tc(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int Cin, int Cout, int k, int u,
+                         TcLayer* L) {
+  if (!tc_plan_convt(Cin, Cout, k, u, L)) return DISSC_OK;
+  const float* w = wm.get(prefix + ".weight")->data;  // (Cin, Cout, k)
+  const int M = L->k;
+  auto packed = pack_weights_tc(*L, [=](int n, int ci, int jp) {
+    const int phase = n / Cout, co = n % Cout;
+    const int jj = phase + (M - 1 - jp) * u;
+    return jj < k ? w[((size_t)ci * Cout + co) * k + jj] : 0.f;
+  }, &L->inv_scale);
+  return tc_upload(g, packed, &L->w);
 }
 
 static int make_convt(dissc_gen* g, const WeightMap& wm, const std::string& prefix, int Cin, int Cout, int k, int u,
@@ -403,9 +491,12 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // bytes of one workspace region: large enough for any stage's tensor in any layout
-// (plain (B,C,T) fp32, blocked f32b [B][C/8][Tr][8] fp32, or an fp16 hi+lo plane pair [B][C/8][Tp][8] x2)
+// (plain (B,C,T) fp32, blocked f32b [B][C/8][Tr][8] fp32, or an fp16 hi+lo plane pair [B][C/8][Tp][8] x2),
+// plus slack: the last frame tile of a transposed conv may read up to 128 rows past a slab (discarded rows).
 static size_t region_bytes(const dissc_gen* g, int B, int T) {
-  size_t mx = (size_t)B * g->cfg.c0 * T * 4;
+  const size_t tp0 = round_up(T, 128) + 2 * kTcHalo;
+  const size_t cin_pad = round_up(g->cfg.model_in_dim, 16);
+  size_t mx = (size_t)B * std::max<size_t>(g->cfg.c0, cin_pad) * tp0 * 4;
   size_t t = T;
   for (int i = 0; i < g->cfg.n_up; ++i) {
     const ConvTLayer& U = g->ups[i];
@@ -413,7 +504,7 @@ static size_t region_bytes(const dissc_gen* g, int B, int T) {
     const size_t tp = round_up(t, 128) + 2 * kTcHalo;
     mx = std::max(mx, (size_t)B * round_up(U.Cout, 8) * tp * 4);
   }
-  return round_up(mx, 1024);
+  return round_up(mx, 1024) + 8192;
 }
 constexpr int kNumRegions = 8;
 
@@ -483,16 +574,46 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
   float* F_up = x_up;
   float* F_r = r;
   float* F_xs = reinterpret_cast<float*>(region(5));
-  struct Planes { __half* hi; __half* lo; };
-  auto planes = [&](int i) { return Planes{reinterpret_cast<__half*>(region(i)), reinterpret_cast<__half*>(region(i) + RS / 2)}; };
-  const Planes P_xt = planes(3), P_up = planes(6), P_r = planes(7);
-
   Launcher L{st, prof};
   const dissc_gen_cfg& c = g->cfg;
   char name[64];
+  const bool tc_all = g->use_tc && g->tc_all;
+  struct Planes { __half* hi; __half* lo; };
+  auto planes = [&](int i) { return Planes{reinterpret_cast<__half*>(region(i)), reinterpret_cast<__half*>(region(i) + RS / 2)}; };
+  // Tensor-core stages: F_up, F_r, F_xs (blocked fp32) in regions 2,4,5; plane pairs P_xt, P_up, P_r in 3,6,7;
+  // with tc_all the stage inputs (leaky-relu'd planes) ping-pong in regions 0,1 and the embedding planes use region 2.
+  const Planes P_xt = planes(3), P_up = planes(6), P_r = planes(7);
+  const Planes P_act[2] = {planes(0), planes(1)};
+  const int Tr0 = (int)round_up(T, 128), Tp0 = Tr0 + 2 * kTcHalo;
 
-  // conv_pre with fused gather/concat; epilogue applies the first stage's leaky-relu (sr/models.py:99,:101)
-  {
+  if (tc_all) {
+    // gather/concat -> split planes (zero halos written by the same kernel)   (sr/models.py:189,:206-215)
+    const Planes P_emb = planes(2);
+    EmbedParams e{};
+    e.code = reinterpret_cast<const long long*>(code); e.f0 = f0; e.spkr = reinterpret_cast<const long long*>(spkr);
+    e.dict_w = g->dict_w; e.spkr_w = g->spkr_w; e.lengths = lengths;
+    e.E = c.embedding_dim; e.f0_ch = c.has_f0 ? c.embedding_dim : -1;
+    e.spk_base = c.has_spkr ? c.embedding_dim + (c.has_f0 ? 1 : 0) : -1;
+    e.Cin = c.model_in_dim; e.B = B; e.C8 = g->pre_tc.Cin_pad / 8; e.T = T; e.Tp = Tp0;
+    e.hi = P_emb.hi; e.lo = P_emb.lo;
+    DISSC_TRY(L.begin("embed", 0));
+    const long long tot = (long long)B * e.C8 * Tp0;
+    tc_embed_planes_kernel<<<(int)std::min<long long>((tot + 255) / 256, 148 * 8), 256, 0, st>>>(e);
+    DISSC_CUDA(cudaGetLastError());
+    DISSC_TRY(launch_zero_halos(P_act[0].hi, P_act[0].lo, B * c.c0 / 8, Tp0, T, st));
+    DISSC_TRY(L.end());
+    L.count += 1;
+    // conv_pre; epilogue applies the first stage's leaky-relu (sr/models.py:99,:101) and writes planes
+    TcParams p{};
+    p.a_hi = P_emb.hi; p.a_lo = P_emb.lo; p.bias = g->pre.bias;
+    p.out_hi = P_act[0].hi; p.out_lo = P_act[0].lo; p.plane_act = 1; p.plane_slope = 0.1f;
+    p.lengths = lengths; p.len_mul = 1;
+    p.B = B; p.T = T; p.Tr = Tr0; p.Tp = Tp0; p.Tp_in = Tp0;
+    DISSC_TRY(L.begin("conv_pre.tc", 2.0 * g->pre.Cin * g->pre.Cout * g->pre.k * (double)T * B));
+    DISSC_TRY(launch_conv_tc(p, g->pre_tc, T, st));
+    DISSC_TRY(L.end());
+  } else {
+    // conv_pre with fused gather/concat; epilogue applies the first stage's leaky-relu (sr/models.py:99,:101)
     ConvParams p{};
     p.code = reinterpret_cast<const long long*>(code);
     p.f0 = f0;
@@ -512,25 +633,43 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     DISSC_TRY(L.end());
   }
 
-  int cur = 0;     // act[cur] holds the (already activated) stage input, plain (B,C,T)
+  int cur = 0;     // act[cur] / P_act[cur] holds the (already activated) stage input
   int Tcur = T;    // time steps at the current rate
   int mul = 1;     // valid length multiplier (product of rates so far)
   for (int i = 0; i < c.n_up; ++i) {
     const ConvTLayer& U = g->ups[i];
+    const int Tin = Tcur;
     const int Tout = (Tcur - 1) * U.u - 2 * U.pad + U.k;
     const bool tc = g->use_tc && g->stage_tc[i];
+    const int Tr_in = (int)round_up(Tin, 128), Tp_in = Tr_in + 2 * kTcHalo;
     const int Tr = (int)round_up(Tout, 128), Tp = Tr + 2 * kTcHalo;
     const int ch = U.Cout;
+    const bool last_stage = (i == c.n_up - 1);
     if (tc) {
-      // zero padding of the three plane pairs this stage uses (halo rows + round-up rows)
+      // zero padding of the plane pairs this stage writes (halo rows + round-up rows)
       DISSC_TRY(L.begin("zero_halos", 0));
       DISSC_TRY(launch_zero_halos(P_up.hi, P_up.lo, B * ch / 8, Tp, Tout, st));
       DISSC_TRY(launch_zero_halos(P_xt.hi, P_xt.lo, B * ch / 8, Tp, Tout, st));
       DISSC_TRY(launch_zero_halos(P_r.hi, P_r.lo, B * ch / 8, Tp, Tout, st));
-      DISSC_TRY(L.end());
       L.count += 2;
+      if (tc_all && !last_stage) {
+        DISSC_TRY(launch_zero_halos(P_act[cur ^ 1].hi, P_act[cur ^ 1].lo, B * ch / 8, Tp, Tout, st));
+        L.count += 1;
+      }
+      DISSC_TRY(L.end());
     }
-    {
+    snprintf(name, sizeof(name), tc_all ? "ups.%d.tc" : "ups.%d", i);
+    DISSC_TRY(L.begin(name, 2.0 * U.Cin * U.Cout * U.k * (double)Tcur * B));
+    if (tc_all) {
+      // polyphase transposed conv on the tensor cores: frames x (phase, channel)
+      TcParams p{};
+      p.a_hi = P_act[cur].hi; p.a_lo = P_act[cur].lo; p.bias = U.bias;
+      p.out_f32b = F_up; p.out_hi = P_up.hi; p.out_lo = P_up.lo; p.plane_act = 1; p.plane_slope = 0.1f;
+      p.lengths = lengths; p.len_mul = mul * U.u;
+      p.B = B; p.T = Tout; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp_in;
+      const int n_frames = (Tout + U.pad - 1) / U.u + 1;
+      DISSC_TRY(launch_conv_tc(p, g->ups_tc[i], n_frames, st));
+    } else {
       ConvTParams p{};
       p.in = act[cur]; p.w = U.w; p.bias = U.bias; p.out = x_up;
       p.lengths = lengths; p.len_mul = mul;
@@ -539,15 +678,12 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
         p.out = nullptr; p.out_f32b = F_up; p.out_hi = P_up.hi; p.out_lo = P_up.lo;
         p.Tr = Tr; p.Tp = Tp; p.halo = kTcHalo; p.plane_slope = 0.1f;
       }
-      snprintf(name, sizeof(name), "ups.%d", i);
-      DISSC_TRY(L.begin(name, 2.0 * U.Cin * U.Cout * U.k * (double)Tcur * B));
       DISSC_TRY(launch_convt(p, U.k, U.u, U.co_tile, st));
-      DISSC_TRY(L.end());
     }
+    DISSC_TRY(L.end());
     Tcur = Tout;
     mul *= U.u;
     float* xs = act[cur ^ 1];  // MRF accumulator (CUDA-core path) / next stage's activated input
-    const bool last_stage = (i == c.n_up - 1);
     const float next_slope = last_stage ? 0.01f : 0.1f;  // sr/models.py:110 vs :101
     for (int j = 0; j < c.n_rk; ++j) {
       for (int m = 0; m < c.n_dil; ++m) {
@@ -558,22 +694,22 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
         if (tc) {
           const Planes rin_p = (m == 0) ? P_up : P_r;
           const float* rin_f = (m == 0) ? F_up : F_r;
-          TcConvParams base{};
+          TcParams base{};
           base.lengths = lengths; base.len_mul = mul;
-          base.B = B; base.T = Tcur; base.Tr = Tr; base.Tp = Tp;
+          base.B = B; base.T = Tcur; base.Tr = Tr; base.Tp = Tp; base.Tp_in = Tp;
           if (c.resblock == 1) {
             // K3: (leaky-relu'd planes) -> dilated conv -> leaky-relu -> planes   (sr/models.py:36-38)
-            TcConvParams p = base;
+            TcParams p = base;
             p.a_hi = rin_p.hi; p.a_lo = rin_p.lo; p.bias = c1.bias;
             p.out_hi = P_xt.hi; p.out_lo = P_xt.lo; p.plane_act = 1; p.plane_slope = 0.1f;
             snprintf(name, sizeof(name), "s%d.rb%d.c1.%d.tc", i, j, m);
             DISSC_TRY(L.begin(name, fl));
-            DISSC_TRY(launch_conv_tc(p, g->rb_tc[i][j][m][0], st));
+            DISSC_TRY(launch_conv_tc(p, g->rb_tc[i][j][m][0], Tcur, st));
             DISSC_TRY(L.end());
           }
           // K4: conv -> + residual [-> MRF accumulate]   (:39-40, :104-109)
           const int which = (c.resblock == 1) ? 1 : 0;
-          TcConvParams q = base;
+          TcParams q = base;
           const Planes qin = (c.resblock == 1) ? P_xt : rin_p;
           q.a_hi = qin.hi; q.a_lo = qin.lo; q.bias = g->rb[i][j][m][which].bias; q.res = rin_f;
           if (!last_m) {
@@ -584,12 +720,16 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
               q.out_f32b = F_xs;
             } else {
               q.div = (float)c.n_rk;
-              q.out_plain = xs; q.plain_act = 1; q.plain_slope = next_slope;
+              if (tc_all && !last_stage) {
+                q.out_hi = P_act[cur ^ 1].hi; q.out_lo = P_act[cur ^ 1].lo; q.plane_act = 1; q.plane_slope = next_slope;
+              } else {
+                q.out_plain = xs; q.plain_act = 1; q.plain_slope = next_slope;
+              }
             }
           }
           snprintf(name, sizeof(name), "s%d.rb%d.c2.%d.tc", i, j, m);
           DISSC_TRY(L.begin(name, fl));
-          DISSC_TRY(launch_conv_tc(q, g->rb_tc[i][j][m][which], st));
+          DISSC_TRY(launch_conv_tc(q, g->rb_tc[i][j][m][which], Tcur, st));
           DISSC_TRY(L.end());
           continue;
         }
@@ -705,16 +845,16 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
             return fail(rc);
           if ((rc = make_conv(g, wm, p + ".convs2." + std::to_string(m), ch, ch, c.rk[j], 1, &g->rb[i][j][m][1])))
             return fail(rc);
-          if ((rc = make_conv_tc(g, wm, p + ".convs1." + std::to_string(m), ch, c.rk[j], c.dil[j][m],
+          if ((rc = make_conv_tc(g, wm, p + ".convs1." + std::to_string(m), ch, ch, c.rk[j], c.dil[j][m],
                                  &g->rb_tc[i][j][m][0])))
             return fail(rc);
-          if ((rc = make_conv_tc(g, wm, p + ".convs2." + std::to_string(m), ch, c.rk[j], 1, &g->rb_tc[i][j][m][1])))
+          if ((rc = make_conv_tc(g, wm, p + ".convs2." + std::to_string(m), ch, ch, c.rk[j], 1, &g->rb_tc[i][j][m][1])))
             return fail(rc);
         } else {
           if ((rc = make_conv(g, wm, p + ".convs." + std::to_string(m), ch, ch, c.rk[j], c.dil[j][m],
                               &g->rb[i][j][m][0])))
             return fail(rc);
-          if ((rc = make_conv_tc(g, wm, p + ".convs." + std::to_string(m), ch, c.rk[j], c.dil[j][m],
+          if ((rc = make_conv_tc(g, wm, p + ".convs." + std::to_string(m), ch, ch, c.rk[j], c.dil[j][m],
                                  &g->rb_tc[i][j][m][0])))
             return fail(rc);
         }
@@ -725,6 +865,19 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
       for (int m = 0; m < c.n_dil; ++m) {
         g->stage_tc[i] = g->stage_tc[i] && g->rb_tc[i][j][m][0].ok && (c.resblock != 1 || g->rb_tc[i][j][m][1].ok);
       }
+  }
+  // conv_pre and the upsamplers on the tensor cores: only when every stage runs there (planes flow end to end)
+  g->tc_all = c.n_up > 0;
+  for (int i = 0; i < c.n_up; ++i) g->tc_all = g->tc_all && g->stage_tc[i];
+  if (g->tc_all) {
+    if ((rc = make_conv_tc(g, wm, "conv_pre", c.model_in_dim, c.c0, 7, 1, &g->pre_tc))) return fail(rc);
+    g->tc_all = g->pre_tc.ok;
+    for (int i = 0; i < c.n_up && g->tc_all; ++i) {
+      if ((rc = make_convt_tc(g, wm, "ups." + std::to_string(i), c.c0 >> i, c.c0 >> (i + 1), c.up_kernels[i],
+                              c.up_rates[i], &g->ups_tc[i])))
+        return fail(rc);
+      g->tc_all = g->ups_tc[i].ok;
+    }
   }
   // conv_post: (1, ch, 7) -> plain (ch, 7)
   {
@@ -953,17 +1106,20 @@ int dissc_conv_transpose1d(const float* in, const float* w_host, const float* bi
 
 int dissc_conv1d_tc(const float* in, const float* w_host, const float* bias_host, const float* res,
                     const float* acc_in, float* out_plain, float* out_raw, float* out_planes, const int32_t* lengths,
-                    int len_mul, int B, int C, int T, int k, int dilation, int pre_act, float pre_slope, int post_act,
-                    float post_slope, float div, void* stream) {
-  DISSC_CHECK(in && w_host && B > 0 && C > 0 && T > 0, DISSC_EINVAL, "bad argument");
+                    int len_mul, int B, int Cin, int Cout, int T, int k, int dilation, int pre_act, float pre_slope,
+                    int post_act, float post_slope, float div, void* stream) {
+  DISSC_CHECK(in && w_host && B > 0 && Cin > 0 && Cout > 0 && T > 0, DISSC_EINVAL, "bad argument");
   TcLayer L;
-  DISSC_CHECK(tc_plan(C, k, dilation, &L), DISSC_EUNSUPPORTED,
-              "no tcgen05 plan for C=%d kernel_size=%d dilation=%d (needs C%%16==0, 16<=C<=256, pad<=%d)", C, k,
-              dilation, kTcHalo);
+  DISSC_CHECK(tc_plan_conv(Cin, Cout, k, dilation, &L), DISSC_EUNSUPPORTED,
+              "no tcgen05 plan for Cin=%d Cout=%d kernel_size=%d dilation=%d (Cout in {16,32,64,128,256} or a "
+              "multiple of 256, padding <= %d)", Cin, Cout, k, dilation, kTcHalo);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Tr = (int)round_up(T, 128), Tp = Tr + 2 * kTcHalo;
-  const size_t plane_elems = (size_t)B * (C / 8) * Tp * 8, f_elems = (size_t)B * (C / 8) * Tr * 8;
-  auto packed = pack_weights_tc(w_host, C, k, L.KB, &L.inv_scale);
+  const int cin8 = L.Cin_pad / 8;
+  const size_t in_elems = (size_t)B * cin8 * Tp * 8 + 4096, plane_elems = (size_t)B * (Cout / 8) * Tp * 8,
+               f_elems = (size_t)B * (Cout / 8) * Tr * 8;
+  auto packed = pack_weights_tc(L, [=](int n, int ci, int j) { return w_host[((size_t)n * Cin + ci) * k + j]; },
+                                &L.inv_scale);
   std::vector<void*> tmp;
   auto dalloc = [&](size_t bytes) -> void* {
     void* d = nullptr;
@@ -973,9 +1129,9 @@ int dissc_conv1d_tc(const float* in, const float* w_host, const float* bias_host
   };
   auto cleanup = [&]() { for (void* d : tmp) cudaFree(d); };
   __half* dw = (__half*)dalloc(packed.size() * 2);
-  float* db = (float*)dalloc((size_t)C * 4);
-  __half* a_hi = (__half*)dalloc(plane_elems * 2);
-  __half* a_lo = (__half*)dalloc(plane_elems * 2);
+  float* db = (float*)dalloc((size_t)Cout * 4);
+  __half* a_hi = (__half*)dalloc(in_elems * 2);
+  __half* a_lo = (__half*)dalloc(in_elems * 2);
   __half* o_hi = (__half*)dalloc(plane_elems * 2);
   __half* o_lo = (__half*)dalloc(plane_elems * 2);
   float* f_res = (float*)dalloc(f_elems * 4);
@@ -986,32 +1142,102 @@ int dissc_conv1d_tc(const float* in, const float* w_host, const float* bias_host
     return set_err(DISSC_ENOMEM, "cudaMalloc failed in dissc_conv1d_tc");
   }
   cudaMemcpyAsync(dw, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, st);
-  std::vector<float> zero_bias(C, 0.f);
-  cudaMemcpyAsync(db, bias_host ? bias_host : zero_bias.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st);
+  std::vector<float> zero_bias(Cout, 0.f);
+  cudaMemcpyAsync(db, bias_host ? bias_host : zero_bias.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice, st);
   // garbage everywhere first: the kernel must not depend on anything but the zeroed halos
-  cudaMemsetAsync(a_hi, 0x7b, plane_elems * 2, st);
-  cudaMemsetAsync(a_lo, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(a_hi, 0x7b, in_elems * 2, st);
+  cudaMemsetAsync(a_lo, 0x7b, in_elems * 2, st);
   cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
   cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
   const int nb = 148 * 4;
-  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, C, T, Tp, pre_act, pre_slope);
-  int rc = launch_zero_halos(a_hi, a_lo, B * C / 8, Tp, T, st);
-  if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * C / 8, Tp, T, st);
-  if (res) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(res, f_res, B, C, T, Tr);
-  if (acc_in) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(acc_in, f_acc, B, C, T, Tr);
+  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, Cin, cin8, T, Tp, pre_act, pre_slope);
+  int rc = launch_zero_halos(a_hi, a_lo, B * cin8, Tp, T, st);
+  if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * Cout / 8, Tp, T, st);
+  if (res) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(res, f_res, B, Cout, T, Tr);
+  if (acc_in) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(acc_in, f_acc, B, Cout, T, Tr);
   L.w = dw;
-  TcConvParams p{};
+  TcParams p{};
   p.a_hi = a_hi; p.a_lo = a_lo; p.bias = db;
   p.res = res ? f_res : nullptr; p.acc_in = acc_in ? f_acc : nullptr;
   p.out_f32b = out_raw ? f_out : nullptr;
   p.out_hi = out_planes ? o_hi : nullptr; p.out_lo = out_planes ? o_lo : nullptr;
   p.out_plain = out_plain;
   p.lengths = lengths; p.len_mul = len_mul;
-  p.B = B; p.T = T; p.Tr = Tr; p.Tp = Tp;
+  p.B = B; p.T = T; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp;
   p.div = div; p.plane_act = post_act; p.plane_slope = post_slope; p.plain_act = post_act; p.plain_slope = post_slope;
-  if (!rc) rc = launch_conv_tc(p, L, st);
-  if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, C, T, Tr);
-  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp);
+  if (!rc) rc = launch_conv_tc(p, L, T, st);
+  if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, Cout, T, Tr);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, Cout, T, Tp);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cleanup();
+  if (rc) return rc;
+  DISSC_CUDA(e);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+int dissc_conv_transpose1d_tc(const float* in, const float* w_host, const float* bias_host, float* out_raw,
+                              float* out_planes, const int32_t* lengths, int len_mul, int B, int Cin, int Cout,
+                              int T_in, int k, int u, float plane_slope, void* stream) {
+  DISSC_CHECK(in && w_host && B > 0 && Cin > 0 && Cout > 0 && T_in > 0 && u > 0, DISSC_EINVAL, "bad argument");
+  DISSC_CHECK(k >= u && (k - u) % 2 == 0, DISSC_EUNSUPPORTED, "conv_transpose1d needs k >= stride and k - stride even");
+  TcLayer L;
+  DISSC_CHECK(tc_plan_convt(Cin, Cout, k, u, &L), DISSC_EUNSUPPORTED,
+              "no tcgen05 plan for conv_transpose1d Cin=%d Cout=%d kernel_size=%d stride=%d", Cin, Cout, k, u);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int pad = (k - u) / 2;
+  const int Tout = (T_in - 1) * u - 2 * pad + k;
+  const int Tr_in = (int)round_up(T_in, 128), Tp_in = Tr_in + 2 * kTcHalo;
+  const int Tr = (int)round_up(Tout, 128), Tp = Tr + 2 * kTcHalo;
+  const int cin8 = L.Cin_pad / 8, M = L.k;
+  const size_t in_elems = (size_t)B * cin8 * Tp_in * 8 + 4096, plane_elems = (size_t)B * (Cout / 8) * Tp * 8,
+               f_elems = (size_t)B * (Cout / 8) * Tr * 8;
+  auto packed = pack_weights_tc(L, [=](int n, int ci, int jp) {
+    const int phase = n / Cout, co = n % Cout;
+    const int jj = phase + (M - 1 - jp) * u;
+    return jj < k ? w_host[((size_t)ci * Cout + co) * k + jj] : 0.f;
+  }, &L.inv_scale);
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    tmp.push_back(d);
+    return d;
+  };
+  auto cleanup = [&]() { for (void* d : tmp) cudaFree(d); };
+  __half* dw = (__half*)dalloc(packed.size() * 2);
+  float* db = (float*)dalloc((size_t)Cout * 4);
+  __half* a_hi = (__half*)dalloc(in_elems * 2);
+  __half* a_lo = (__half*)dalloc(in_elems * 2);
+  __half* o_hi = (__half*)dalloc(plane_elems * 2);
+  __half* o_lo = (__half*)dalloc(plane_elems * 2);
+  float* f_out = (float*)dalloc(f_elems * 4);
+  if (!dw || !db || !a_hi || !a_lo || !o_hi || !o_lo || !f_out) {
+    cleanup();
+    return set_err(DISSC_ENOMEM, "cudaMalloc failed in dissc_conv_transpose1d_tc");
+  }
+  cudaMemcpyAsync(dw, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, st);
+  std::vector<float> zero_bias(Cout, 0.f);
+  cudaMemcpyAsync(db, bias_host ? bias_host : zero_bias.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(a_hi, 0x7b, in_elems * 2, st);
+  cudaMemsetAsync(a_lo, 0x7b, in_elems * 2, st);
+  cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(f_out, 0x7b, f_elems * 4, st);
+  const int nb = 148 * 4;
+  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, Cin, cin8, T_in, Tp_in, 0, 0.f);
+  int rc = launch_zero_halos(a_hi, a_lo, B * cin8, Tp_in, T_in, st);
+  if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * Cout / 8, Tp, Tout, st);
+  L.w = dw;
+  TcParams p{};
+  p.a_hi = a_hi; p.a_lo = a_lo; p.bias = db;
+  p.out_f32b = f_out; p.out_hi = o_hi; p.out_lo = o_lo; p.plane_act = 1; p.plane_slope = plane_slope;
+  p.lengths = lengths; p.len_mul = len_mul * u;
+  p.B = B; p.T = Tout; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp_in;
+  const int n_frames = (Tout + pad - 1) / u + 1;
+  if (!rc) rc = launch_conv_tc(p, L, n_frames, st);
+  if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, Cout, Tout, Tr);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, Cout, Tout, Tp);
   cudaError_t e = cudaStreamSynchronize(st);
   cleanup();
   if (rc) return rc;

@@ -152,11 +152,12 @@ def test_unsupported_geometry_fails_loudly(cuda_device):
 # ---------------------------------------------------------------------------------------------
 # tensor-core (tcgen05, split-fp16) twin of the fused conv
 # ---------------------------------------------------------------------------------------------
-def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0, wscale=1.0):
+def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0, wscale=1.0, Cin=None):
     from dissc_b200 import _lib
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(B, C, T, generator=g)
-    w = wscale * torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    Cin = Cin or C
+    x = torch.randn(B, Cin, T, generator=g)
+    w = wscale * torch.randn(C, Cin, k, generator=g) / (Cin * k) ** 0.5
     b = torch.randn(C, generator=g)
     r = torch.randn(B, C, T, generator=g) if res else None
     a = torch.randn(B, C, T, generator=g) if acc else None
@@ -185,7 +186,7 @@ def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0,
     ad = None if a is None else a.to(dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().dissc_conv1d_tc(_ptr(xd), _ptr(w), _ptr(b), _ptr(rd), _ptr(ad), _ptr(outs[0]),
-                                               _ptr(outs[1]), _ptr(outs[2]), _ptr(ld), 1, B, C, T, k, d, int(pre), 0.1,
+                                               _ptr(outs[1]), _ptr(outs[2]), _ptr(ld), 1, B, Cin, C, T, k, d, int(pre), 0.1,
                                                int(post), 0.01, float(div), None))
     torch.cuda.synchronize()
     scale = max(1.0, wscale)
@@ -237,3 +238,58 @@ def test_tc_conv_lengths_mask(cuda_device):
 def test_tc_conv_weight_scaling(cuda_device, wscale):
     # the power-of-two pre-scale keeps the fp16 split accurate whatever the weight magnitude
     _tc_case(cuda_device, 1, 64, 300, 7, 1, pre=False, post=False, res=False, acc=False, div=0, wscale=wscale)
+
+
+@pytest.mark.parametrize("Cin,Cout", [(257, 512), (17, 32), (40, 16), (272, 256)])
+def test_tc_conv_cin_neq_cout_chunked(cuda_device, Cin, Cout):
+    # conv_pre geometry: ragged Cin (zero-padded to 16), Cout > 256 split into 256-column chunks
+    _tc_case(cuda_device, 2, Cout, 300, 7, 1, pre=False, post=True, res=False, acc=False, div=0, Cin=Cin)
+
+
+def _tc_convt_case(dev, B, Cin, Cout, k, u, T, lengths=None, seed=0):
+    from dissc_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, k, generator=g) / (Cin * k / u) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xin = x.clone()
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xin[i, :, n:] = 0
+    pad = (k - u) // 2
+    want = F.conv_transpose1d(xin.double(), w.double(), b.double(), stride=u, padding=pad).float()
+    Tout = want.shape[-1]
+    xd = x.to(dev)
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xd[i, :, n:] = float("nan")
+    raw = torch.full((B, Cout, Tout), float("nan"), device=dev)
+    pl = torch.full((B, Cout, Tout), float("nan"), device=dev)
+    ld = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dissc_conv_transpose1d_tc(_ptr(xd), _ptr(w), _ptr(b), _ptr(raw), _ptr(pl), _ptr(ld), 1,
+                                                         B, Cin, Cout, T, k, u, 0.1, None))
+    torch.cuda.synchronize()
+    raw, pl = raw.cpu(), pl.cpu()
+    wantp = F.leaky_relu(want, 0.1)
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            assert torch.all(pl[i, :, n * u:] == 0), "rows past the valid length must be stored as zeros"
+            raw[i, :, n * u:] = 0
+            want[i, :, n * u:] = 0
+            wantp[i, :, n * u:] = 0
+    assert torch.isfinite(raw).all() and torch.isfinite(pl).all()
+    assert (raw - want).abs().max().item() < 2e-5
+    assert (pl - wantp).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,k,u,T", [
+    (512, 256, 11, 5, 300), (256, 128, 8, 4, 640), (128, 64, 8, 4, 1500), (64, 32, 4, 2, 3000), (32, 16, 4, 2, 5000),
+    (32, 16, 16, 8, 257), (32, 256, 11, 5, 1), (64, 64, 8, 4, 128), (48, 16, 4, 2, 129)])
+def test_tc_conv_transpose1d(cuda_device, Cin, Cout, k, u, T):
+    _tc_convt_case(cuda_device, 2, Cin, Cout, k, u, T)
+
+
+def test_tc_conv_transpose1d_lengths(cuda_device):
+    _tc_convt_case(cuda_device, 3, 64, 32, 8, 4, 300, lengths=[300, 1, 129])
+    _tc_convt_case(cuda_device, 2, 512, 256, 11, 5, 128, lengths=[128, 77])
