@@ -214,26 +214,43 @@ def main():
         dist.destroy_process_group()
     if rank != 0:
         return
-    # ---- roofline: algorithmic bytes of the fused forward / measured step time -------------
+    # ---- roofline -------------------------------------------------------------------------
+    # Dominant kernel = conv_tc_kernel (every conv but conv_post).  achieved = the algorithmic bytes of its launches
+    # (layer-fused traffic model, SURVEY.md 8d / DESIGN.md) / their summed CUDA-event durations, measured on one extra
+    # forward with an event pair around every launch on the launching stream.  `forward` is the same figure for the
+    # whole step over the timed region.
     flops, abytes = gen.cost(B, T, dev)
     peak_gbs, sm_max_mhz, peak_src = measured_peaks()
-    ach = abytes / (ms_step * 1e-3) / 1e9
-    fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     rows = gen.profile(code, f0, spkr)  # one extra, untimed forward with an event pair around every launch
     fam = {}
-    for name, ms, fl in rows:
-        key = "convt1d_kernel" if name.startswith("ups") else "conv_post_kernel" if name == "conv_post" \
-            else "conv1d_fused_kernel"
-        a = fam.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0})
+    for name, ms, fl, by in rows:
+        key = "conv_tc_kernel" if name.endswith(".tc") else "conv_post_kernel" if name == "conv_post" \
+            else "convt1d_kernel" if name.startswith("ups") else "tc_embed_planes+tc_zero_halos" \
+            if name in ("embed", "zero_halos") else "conv1d_fused_kernel"
+        a = fam.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         a["launches"] += 1
         a["ms"] += ms
         a["flops"] += fl
+        a["bytes"] += by
     tot_ms = sum(a["ms"] for a in fam.values())
     for a in fam.values():
-        a["share"] = a["ms"] / tot_ms
-        a["tflops"] = a["flops"] / a["ms"] / 1e9
+        a["share"] = round(a["ms"] / tot_ms, 4)
+        a["tflops"] = round(a["flops"] / a["ms"] / 1e9, 2)
+        a["algorithmic_gbs"] = round(a["bytes"] / a["ms"] / 1e6, 1)
         a["ms"] = round(a["ms"], 3)
-        del a["flops"]
+        del a["flops"], a["bytes"]
+    dom_name = max(fam, key=lambda k: fam[k]["ms"])
+    dom = fam[dom_name]
+    dom_rows = [r for r in rows if (r[0].endswith(".tc") if dom_name == "conv_tc_kernel" else True)]
+    dom_bytes = sum(r[3] for r in dom_rows)
+    dom_ms = sum(r[1] for r in dom_rows)
+    dom_flops = sum(r[2] for r in dom_rows)
+    ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    fwd_ach = abytes / (ms_step * 1e-3) / 1e9
+    split_tflops = 3.0 * dom_flops / (dom_ms * 1e-3) / 1e12   # three fp16 MMAs per fp32-accurate product
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -241,6 +258,7 @@ def main():
         "config": {"workload": f"CodeGenerator forward, batch={B} VCTK-shape utterances x {T} units "
                                f"(x{gen.hop} -> {gen.hop * T} samples each) per GPU (BASELINE configs[1])",
                    "weights": "seeded synthetic checkpoint, shipped VCTK geometry (13.7M params)",
+                   "arithmetic": "fp32 results (<=2e-5 max-abs vs fp64) from split-fp16 tcgen05 MMAs, fp32 accumulate",
                    "l2": "every layer's working set (>=0.8 GB at B=64) exceeds the 126 MB L2; no flush needed",
                    "parallelism": f"utterance-sharded x{world}"},
         "clocks": clocks,
@@ -250,12 +268,18 @@ def main():
         "gpu_launches": gen.launches_per_forward() * args.steps,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                      "traffic": None, "peak_source": peak_src,
-                     "kernel": "fused Generator forward (97 launches; conv1d_fused_kernel dominates)",
-                     "algorithmic_bytes_per_step": abytes,
-                     "binding_roof": "fp32 FMA pipe (dense contraction, 85 FLOP/B): see fp32_pipe",
-                     "fp32_pipe": {"achieved_tflops": flops / (ms_step * 1e-3) / 1e12, "peak_tflops": fp32_peak,
-                                   "frac": flops / (ms_step * 1e-3) / 1e12 / fp32_peak,
-                                   "peak_source": f"148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz"},
+                     "kernel": f"{dom_name} ({dom['launches']} of {len(rows)} launches per forward, "
+                               f"{100 * dom['share']:.1f}% of the step)",
+                     "algorithmic_bytes_per_launch_avg": dom_bytes / max(1, len(dom_rows)),
+                     "launch_ms_avg": dom_ms / max(1, len(dom_rows)),
+                     "forward": {"achieved": fwd_ach, "frac": fwd_ach / peak_gbs, "algorithmic_bytes_per_step": abytes,
+                                 "note": "whole step over the timed region (all kernels)"},
+                     "binding_roof": "tensor pipe for stages 0-2 (dense contraction, 85 FLOP/B), HBM/latency for "
+                                     "stages 3-4: see tensor_pipe",
+                     "tensor_pipe": {"achieved_tflops_fp32_equivalent": dom_flops / (dom_ms * 1e-3) / 1e12,
+                                     "achieved_tflops_fp16_mma": split_tflops, "peak_tflops": tensor_peak,
+                                     "frac": split_tflops / tensor_peak,
+                                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16)"},
                      "kernels": fam},
     }
     if world == 1 and not args.no_cpu_baseline:

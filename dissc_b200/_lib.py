@@ -40,7 +40,7 @@ EXPORTS = [
     "dissc_gen_create", "dissc_gen_destroy", "dissc_gen_hop", "dissc_gen_workspace_bytes", "dissc_gen_forward",
     "dissc_gen_forward_i16", "dissc_gen_forward_host", "dissc_gen_launches_per_forward", "dissc_gen_cost",
     "dissc_gen_profile", "dissc_conv1d_fused", "dissc_conv_transpose1d", "dissc_last_error", "dissc_version",
-    "dissc_gen_set_tensor_cores", "dissc_gen_tensor_core_stages", "dissc_conv1d_tc", "dissc_conv_transpose1d_tc",
+    "dissc_gen_set_tensor_cores", "dissc_gen_tensor_core_stages", "dissc_conv1d_tc", "dissc_conv_transpose1d_tc", "dissc_tc_set_single_accumulator",
 ]
 
 
@@ -68,8 +68,8 @@ def lib():
                                          c_void_p]
     L.dissc_gen_cost.argtypes = [c_void_p, c_int, c_int, POINTER(c_double), POINTER(c_double)]
     L.dissc_gen_profile.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                                    c_void_p, c_size_t, c_void_p, POINTER(c_float), POINTER(c_double), c_int,
-                                    POINTER(c_int)]
+                                    c_void_p, c_size_t, c_void_p, POINTER(c_float), POINTER(c_double),
+                                    POINTER(c_double), c_int, POINTER(c_int)]
     L.dissc_conv1d_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                      c_float, c_void_p]
@@ -77,6 +77,7 @@ def lib():
                                          c_int, c_int, c_int, c_int, c_void_p]
     L.dissc_gen_set_tensor_cores.argtypes = [c_void_p, c_int]
     L.dissc_gen_tensor_core_stages.argtypes = [c_void_p]
+    L.dissc_tc_set_single_accumulator.argtypes = [c_int]
     L.dissc_conv1d_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                   c_float, c_float, c_void_p]

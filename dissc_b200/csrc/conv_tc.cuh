@@ -139,11 +139,12 @@ __device__ __forceinline__ void split_store8(__half* hi_dst, __half* lo_dst, con
 }
 
 template <int NC>
-__global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC == 64) ? 2 : 1)) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 : 1)) conv_tc_kernel(const TcParams p) {
   constexpr bool kTwoMma = (NC <= 128);
   constexpr int G = NC / 8;            // 8-channel groups per chunk
   constexpr int EB = 2;                // groups per epilogue batch
   constexpr int NB = G / EB;
+  constexpr bool kAccPrefetch = (NC >= 64);  // MRF accumulator prefetched like the residual (registers permitting)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int R = 128 + (p.k - 1) * p.dil;                          // activation rows a tile needs
   const uint32_t lbo_a = (uint32_t)R * 16;                        // bytes between 8-channel chunks of A
@@ -312,11 +313,19 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC == 64) ? 2 :
       const bool conv_valid = (!p.up) && r < Tvalid;
       const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * G) * p.Tr + r) * 8;  // conv mode only
       const size_t fstride = (size_t)p.Tr * 8;
+      float4 aq[EB * 2];
       if (p.res && conv_valid) {
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
           rq[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + e * fstride);
           rq[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + e * fstride + 4);
+        }
+      }
+      if (kAccPrefetch && p.acc_in && conv_valid) {
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+          aq[2 * e] = *reinterpret_cast<const float4*>(p.acc_in + fbase + e * fstride);
+          aq[2 * e + 1] = *reinterpret_cast<const float4*>(p.acc_in + fbase + e * fstride + 4);
         }
       }
       mbar_wait(&acc_full[ab], accph);
@@ -337,6 +346,14 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC == 64) ? 2 :
           for (int e = 0; e < EB; ++e) {
             rn[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + ((bi + 1) * EB + e) * fstride);
             rn[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + ((bi + 1) * EB + e) * fstride + 4);
+          }
+        }
+        float4 an[EB * 2];
+        if (kAccPrefetch && NB > 1 && bi + 1 < NB && p.acc_in && conv_valid) {
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
+            an[2 * e] = *reinterpret_cast<const float4*>(p.acc_in + fbase + ((bi + 1) * EB + e) * fstride);
+            an[2 * e + 1] = *reinterpret_cast<const float4*>(p.acc_in + fbase + ((bi + 1) * EB + e) * fstride + 4);
           }
         }
         tmem_ld_wait();
@@ -372,8 +389,13 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC == 64) ? 2 :
               v[4] += rq[2 * e + 1].x; v[5] += rq[2 * e + 1].y; v[6] += rq[2 * e + 1].z; v[7] += rq[2 * e + 1].w;
             }
             if (p.acc_in) {
-              const float4 r0 = *reinterpret_cast<const float4*>(p.acc_in + fidx);
-              const float4 r1 = *reinterpret_cast<const float4*>(p.acc_in + fidx + 4);
+              float4 r0, r1;
+              if constexpr (kAccPrefetch) {
+                r0 = aq[2 * e]; r1 = aq[2 * e + 1];
+              } else {
+                r0 = *reinterpret_cast<const float4*>(p.acc_in + fidx);
+                r1 = *reinterpret_cast<const float4*>(p.acc_in + fidx + 4);
+              }
               v[0] = r0.x + v[0]; v[1] = r0.y + v[1]; v[2] = r0.z + v[2]; v[3] = r0.w + v[3];
               v[4] = r1.x + v[4]; v[5] = r1.y + v[5]; v[6] = r1.z + v[6]; v[7] = r1.w + v[7];
             }
@@ -402,7 +424,10 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC == 64) ? 2 :
         }
         if (NB > 1) {
 #pragma unroll
-          for (int e = 0; e < EB * 2; ++e) rq[e] = rn[e];
+          for (int e = 0; e < EB * 2; ++e) {
+            rq[e] = rn[e];
+            if constexpr (kAccPrefetch) aq[e] = an[e];
+          }
         }
       }
       tc_fence_before();

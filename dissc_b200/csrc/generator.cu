@@ -173,7 +173,9 @@ struct TcLayer {
 };
 
 constexpr size_t kSmemPerSm = 227 * 1024;
-static int g_single_acc256 = -1;  // NC == 256: one accumulator (double-buffered TMEM) instead of main+cross
+// NC == 256: one accumulator (so TMEM double-buffers) instead of main+cross.  Measured end to end (profiles/README.md):
+// 1.8e-5 max-abs vs fp64 instead of 7e-6, stage 0 23 % faster.  DISSC_TC_SINGLE_ACC=0 restores the dual accumulator.
+static int g_single_acc256 = -1;
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
 static bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L) {
@@ -190,7 +192,7 @@ static bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L) 
   }
   if (g_single_acc256 < 0) {
     const char* e = getenv("DISSC_TC_SINGLE_ACC");
-    g_single_acc256 = e ? (atoi(e) != 0) : 0;
+    g_single_acc256 = e ? (atoi(e) != 0) : 1;
   }
   L->Cin = Cin; L->Cin_pad = (Cin + 15) / 16 * 16; L->NC = NC; L->n_chunks = ncols / NC;
   L->k = taps; L->dil = dil; L->pad = pad;
@@ -210,7 +212,7 @@ static bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L) 
   L->SPC = (taps + L->JG - 1) / L->JG;
   const size_t slot = (size_t)L->JG * w_tap;
   const int total_slots = L->n_cb * L->SPC;
-  int cap = NC <= 32 ? 3 : (NC == 64 ? 2 : 1);  // matches __launch_bounds__ of conv_tc_kernel<NC>
+  int cap = NC <= 32 ? 3 : (NC <= 64 ? 2 : 1);  // matches __launch_bounds__ of conv_tc_kernel<NC>
   cap = std::min(cap, 512 / cols);
   for (int ctas = cap; ctas >= 1; --ctas) {
     const size_t budget = kSmemPerSm / ctas - 1536;  // static shared + alignment + per-CTA reservation
@@ -366,6 +368,7 @@ struct Profiler {
   char (*names)[64];
   float* ms;
   double* flops;
+  double* bytes;  // algorithmic bytes of the launch (layer-fused traffic model)
   int cap;
   int n = 0;
   std::vector<cudaEvent_t> ev;
@@ -518,12 +521,13 @@ struct Launcher {
   cudaStream_t st;
   Profiler* prof;
   int count = 0;
-  int begin(const char* name, double flops) {
+  int begin(const char* name, double flops, double bytes = 0.0) {
     ++count;
     if (!prof) return DISSC_OK;
     if (prof->n >= prof->cap) return set_err(DISSC_EINVAL, "profile capacity %d too small", prof->cap);
     snprintf(prof->names[prof->n], 64, "%s", name);
     prof->flops[prof->n] = flops;
+    if (prof->bytes) prof->bytes[prof->n] = bytes;
     cudaEvent_t e0, e1;
     DISSC_CUDA(cudaEventCreate(&e0));
     DISSC_CUDA(cudaEventCreate(&e1));
@@ -609,7 +613,8 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     p.out_hi = P_act[0].hi; p.out_lo = P_act[0].lo; p.plane_act = 1; p.plane_slope = 0.1f;
     p.lengths = lengths; p.len_mul = 1;
     p.B = B; p.T = T; p.Tr = Tr0; p.Tp = Tp0; p.Tp_in = Tp0;
-    DISSC_TRY(L.begin("conv_pre.tc", 2.0 * g->pre.Cin * g->pre.Cout * g->pre.k * (double)T * B));
+    DISSC_TRY(L.begin("conv_pre.tc", 2.0 * g->pre.Cin * g->pre.Cout * g->pre.k * (double)T * B,
+                      (8.0 + (c.has_f0 ? 4.0 : 0.0)) * T * B + (c.has_spkr ? 8.0 * B : 0.0) + 4.0 * g->pre.Cout * (double)T * B + 4.0 * g->pre.Cin * g->pre.Cout * g->pre.k));
     DISSC_TRY(launch_conv_tc(p, g->pre_tc, T, st));
     DISSC_TRY(L.end());
   } else {
@@ -628,7 +633,8 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     p.B = B; p.Cin = g->pre.Cin; p.Cout = g->pre.Cout; p.T = T; p.pad = g->pre.pad;
     p.post_act = 1; p.post_slope = 0.1f;
     if (c.n_up == 0) { p.post_slope = 0.01f; }
-    DISSC_TRY(L.begin("conv_pre", 2.0 * p.Cin * p.Cout * g->pre.k * (double)T * B));
+    DISSC_TRY(L.begin("conv_pre", 2.0 * p.Cin * p.Cout * g->pre.k * (double)T * B,
+                      (8.0 + (c.has_f0 ? 4.0 : 0.0)) * T * B + (c.has_spkr ? 8.0 * B : 0.0) + 4.0 * g->pre.Cout * (double)T * B + 4.0 * g->pre.Cin * g->pre.Cout * g->pre.k));
     DISSC_TRY(launch_conv(p, g->pre.k, 1, g->pre.co_tile, true, st));
     DISSC_TRY(L.end());
   }
@@ -659,7 +665,8 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
       DISSC_TRY(L.end());
     }
     snprintf(name, sizeof(name), tc_all ? "ups.%d.tc" : "ups.%d", i);
-    DISSC_TRY(L.begin(name, 2.0 * U.Cin * U.Cout * U.k * (double)Tcur * B));
+    DISSC_TRY(L.begin(name, 2.0 * U.Cin * U.Cout * U.k * (double)Tcur * B,
+                      4.0 * B * ((double)U.Cin * Tin + (double)U.Cout * Tout) + 4.0 * U.Cin * U.Cout * U.k));
     if (tc_all) {
       // polyphase transposed conv on the tensor cores: frames x (phase, channel)
       TcParams p{};
@@ -691,6 +698,9 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
         const bool last_j = (j == c.n_rk - 1);
         const ConvLayer& c1 = g->rb[i][j][m][0];
         const double fl = 2.0 * ch * ch * (double)c1.k * Tcur * B;
+        const double S = 4.0 * ch * (double)Tcur * B, wb = 4.0 * ch * ch * (double)c1.k;
+        const double by1 = 2 * S + wb;                                                       // K3: 1R + 1W
+        const double by2 = 3 * S + wb + ((m == c.n_dil - 1 && j > 0) ? S : 0.0);             // K4: 2R + 1W (+ xs read)
         if (tc) {
           const Planes rin_p = (m == 0) ? P_up : P_r;
           const float* rin_f = (m == 0) ? F_up : F_r;
@@ -703,7 +713,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
             p.a_hi = rin_p.hi; p.a_lo = rin_p.lo; p.bias = c1.bias;
             p.out_hi = P_xt.hi; p.out_lo = P_xt.lo; p.plane_act = 1; p.plane_slope = 0.1f;
             snprintf(name, sizeof(name), "s%d.rb%d.c1.%d.tc", i, j, m);
-            DISSC_TRY(L.begin(name, fl));
+            DISSC_TRY(L.begin(name, fl, by1));
             DISSC_TRY(launch_conv_tc(p, g->rb_tc[i][j][m][0], Tcur, st));
             DISSC_TRY(L.end());
           }
@@ -728,7 +738,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
             }
           }
           snprintf(name, sizeof(name), "s%d.rb%d.c2.%d.tc", i, j, m);
-          DISSC_TRY(L.begin(name, fl));
+          DISSC_TRY(L.begin(name, fl, by2));
           DISSC_TRY(launch_conv_tc(q, g->rb_tc[i][j][m][which], Tcur, st));
           DISSC_TRY(L.end());
           continue;
@@ -742,7 +752,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
           p.in = rin; p.w = c1.w; p.bias = c1.bias; p.out = xt; p.pad = c1.pad;
           p.pre_act = 1; p.pre_slope = 0.1f; p.post_act = 1; p.post_slope = 0.1f;
           snprintf(name, sizeof(name), "s%d.rb%d.c1.%d", i, j, m);
-          DISSC_TRY(L.begin(name, fl));
+          DISSC_TRY(L.begin(name, fl, by1));
           DISSC_TRY(launch_conv(p, c1.k, c1.dil, c1.co_tile, false, st));
           DISSC_TRY(L.end());
         }
@@ -768,7 +778,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
           }
         }
         snprintf(name, sizeof(name), "s%d.rb%d.c2.%d", i, j, m);
-        DISSC_TRY(L.begin(name, fl));
+        DISSC_TRY(L.begin(name, fl, by2));
         DISSC_TRY(launch_conv(q, c2.k, c2.dil, c2.co_tile, false, st));
         DISSC_TRY(L.end());
       }
@@ -782,7 +792,8 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     p.out_f32 = out_f32; p.out_i16 = out_i16;
     p.lengths = lengths; p.len_mul = mul;
     p.B = B; p.Cin = g->post.Cin; p.T = Tcur;
-    DISSC_TRY(L.begin("conv_post", 2.0 * p.Cin * g->post.k * (double)Tcur * B));
+    DISSC_TRY(L.begin("conv_post", 2.0 * p.Cin * g->post.k * (double)Tcur * B,
+                      4.0 * B * ((double)p.Cin * Tcur + Tcur) + 4.0 * p.Cin * g->post.k));
     DISSC_TRY(launch_conv_post(p, g->post.k, st));
     DISSC_TRY(L.end());
   }
@@ -924,6 +935,12 @@ int dissc_gen_set_tensor_cores(dissc_gen_t* g, int enable) {
   return DISSC_OK;
 }
 
+int dissc_tc_set_single_accumulator(int enable) {
+  const int prev = g_single_acc256;
+  g_single_acc256 = enable ? 1 : 0;
+  return prev;
+}
+
 int dissc_gen_tensor_core_stages(const dissc_gen_t* g) {
   if (!g || !g->use_tc) return 0;
   int n = 0;
@@ -1032,9 +1049,9 @@ int dissc_gen_cost(const dissc_gen_t* g, int B, int T, double* flops, double* by
 
 int dissc_gen_profile(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
                       const int32_t* lengths, int B, int T, float* out, void* workspace, size_t workspace_bytes,
-                      char (*names)[64], float* ms, double* flops, int cap, int* n) {
+                      char (*names)[64], float* ms, double* flops, double* bytes, int cap, int* n) {
   DISSC_CHECK(names && ms && flops && n, DISSC_EINVAL, "null profile arrays");
-  Profiler prof{names, ms, flops, cap};
+  Profiler prof{names, ms, flops, bytes, cap};
   int rc = forward_impl(g, code, f0, spkr, lengths, B, T, out, nullptr, workspace, workspace_bytes, nullptr, &prof);
   cudaError_t e = cudaDeviceSynchronize();
   if (rc == DISSC_OK && e == cudaSuccess)

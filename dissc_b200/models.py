@@ -328,7 +328,7 @@ class CodeGenerator(nn.Module):
         return fl.value, by.value
 
     def profile(self, code, f0, spkr, lengths=None):
-        """Per-launch device times of one forward: list of (name, ms, flops)."""
+        """Per-launch device times of one forward: list of (name, ms, flops, algorithmic bytes)."""
         B, T = code.shape
         dev = code.device
         L = _lib.lib()
@@ -340,6 +340,7 @@ class CodeGenerator(nn.Module):
         names = ((ctypes.c_char * 64) * cap)()
         ms = (ctypes.c_float * cap)()
         fl = (ctypes.c_double * cap)()
+        by = (ctypes.c_double * cap)()
         n = ctypes.c_int()
         ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
         f0 = None if f0 is None else f0.reshape(B, T).float().contiguous()
@@ -347,5 +348,5 @@ class CodeGenerator(nn.Module):
         torch.cuda.synchronize(dev)
         with torch.cuda.device(dev):
             _lib.check(L.dissc_gen_profile(h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T, ptr(out), ptr(ws),
-                                           need, names, ms, fl, cap, ctypes.byref(n)), "dissc_gen_profile")
-        return [(names[i].value.decode(), ms[i], fl[i]) for i in range(n.value)]
+                                           need, names, ms, fl, by, cap, ctypes.byref(n)), "dissc_gen_profile")
+        return [(names[i].value.decode(), ms[i], fl[i], by[i]) for i in range(n.value)]

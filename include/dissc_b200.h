@@ -125,6 +125,12 @@ int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0,
 int dissc_gen_set_tensor_cores(dissc_gen_t* g, int enable);
 int dissc_gen_tensor_core_stages(const dissc_gen_t* g); /* how many stages currently take the tensor-core path */
 
+/* N=256 tensor-core layers: 1 (default) = the three split-precision MMAs share ONE TMEM accumulator, which leaves
+ * room to double-buffer tiles (stage 0 runs 23 % faster; waveform error 1.8e-5 max-abs vs fp64); 0 = separate main and
+ * cross-term accumulators (7e-6).  Applies to handles / layer calls created afterwards.  Returns the previous setting
+ * (-1 = never set: env DISSC_TC_SINGLE_ACC or the default decides). */
+int dissc_tc_set_single_accumulator(int enable);
+
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
 int dissc_gen_launches_per_forward(const dissc_gen_t* g);
 
@@ -132,11 +138,12 @@ int dissc_gen_launches_per_forward(const dissc_gen_t* g);
 int dissc_gen_cost(const dissc_gen_t* g, int B, int T, double* flops, double* bytes);
 
 /* Per-layer device timing of one forward (cudaEvent around every launch; debug /
- * profiling aid).  names/ms are caller arrays of capacity `cap`; *n receives
- * the number of launches.  Synchronises. */
+ * profiling aid).  names/ms/flops/bytes are caller arrays of capacity `cap`
+ * (bytes may be NULL; it receives each launch's algorithmic bytes under the
+ * layer-fused traffic model); *n receives the number of launches.  Synchronises. */
 int dissc_gen_profile(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
                       const int32_t* lengths, int B, int T, float* out, void* workspace, size_t workspace_bytes,
-                      char (*names)[64], float* ms, double* flops, int cap, int* n);
+                      char (*names)[64], float* ms, double* flops, double* bytes, int cap, int* n);
 
 /* ------------------------------------------------------------------ *
  * Generic fused layers (exposed for layer-level parity tests)

@@ -28,8 +28,8 @@ def main():
     rows = gen.profile(code, f0, spkr)
     tot = sum(r[1] for r in rows)
     agg = {}
-    for name, ms, fl in rows:
-        print(f"{name:16s} {ms:8.3f} ms  {fl / ms / 1e9 if ms > 0 else 0:8.2f} TFLOP/s")
+    for name, ms, fl, by in rows:
+        print(f"{name:16s} {ms:8.3f} ms  {fl / ms / 1e9 if ms > 0 else 0:8.2f} TFLOP/s  {by / ms / 1e6 if ms > 0 else 0:8.1f} GB/s (algorithmic)")
         key = name.split(".")[0] if name.startswith("s") else name.split(".")[0]
         a = agg.setdefault(key, [0.0, 0.0])
         a[0] += ms
