@@ -22,6 +22,7 @@
 #include "conv_tc.cuh"
 #include "conv_post.cuh"
 #include "convt1d.cuh"
+#include "launch.cuh"
 
 namespace dissc {
 
@@ -39,8 +40,7 @@ int set_err(int code, const char* fmt, ...) {
 // weight packing (host)
 // ------------------------------------------------------------------------
 // -> [co_tile][chunk][CI_CHUNK][k][CO_TILE], zero padded.  transposed: source is (Cin,Cout,k).
-static std::vector<float> pack_weights(const float* w, int Cin, int Cout, int k, int co_tile, int ci_chunk,
-                                       bool transposed) {
+std::vector<float> pack_weights(const float* w, int Cin, int Cout, int k, int co_tile, int ci_chunk, bool transposed) {
   const int n_cot = (Cout + co_tile - 1) / co_tile;
   const int n_chunk = (Cin + ci_chunk - 1) / ci_chunk;
   std::vector<float> out((size_t)n_cot * n_chunk * ci_chunk * k * co_tile, 0.f);
@@ -60,8 +60,8 @@ static std::vector<float> pack_weights(const float* w, int Cin, int Cout, int k,
   return out;
 }
 
-static int conv_co_tile(int Cout) { return Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16); }
-static int conv_ci_chunk(int co_tile) { return co_tile == 16 ? 4 : 8; }
+int conv_co_tile(int Cout) { return Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16); }
+int conv_ci_chunk(int co_tile) { return co_tile == 16 ? 4 : 8; }
 static int convt_co_tile(int Cout) { return Cout >= 32 ? 32 : 16; }
 
 // ------------------------------------------------------------------------
@@ -103,12 +103,12 @@ static int launch_conv_cot(const ConvParams& p, int k, int dil, bool emb, cudaSt
   return set_err(DISSC_EUNSUPPORTED, "conv1d kernel_size=%d dilation=%d has no sm_100a instantiation", k, dil);
 }
 
-static bool conv_supported(int k, int dil) {
+bool conv_supported(int k, int dil) {
   if (k == 1) return dil == 1;
   return (k == 3 || k == 5 || k == 7 || k == 11) && (dil == 1 || dil == 3 || dil == 5);
 }
 
-static int launch_conv(const ConvParams& p, int k, int dil, int co_tile, bool emb, cudaStream_t st) {
+int launch_conv(const ConvParams& p, int k, int dil, int co_tile, bool emb, cudaStream_t st) {
   switch (co_tile) {
     case 64: return launch_conv_cot<64, 8>(p, k, dil, emb, st);
     case 32: return launch_conv_cot<32, 8>(p, k, dil, emb, st);

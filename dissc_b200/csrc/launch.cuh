@@ -1,0 +1,18 @@
+// Host-side launch helpers shared between translation units (defined in generator.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "conv1d.cuh"
+
+namespace dissc {
+
+// -> [co_tile][chunk][CI_CHUNK][k][CO_TILE], zero padded.  transposed: source is (Cin,Cout,k).
+std::vector<float> pack_weights(const float* w, int Cin, int Cout, int k, int co_tile, int ci_chunk, bool transposed);
+int conv_co_tile(int Cout);
+int conv_ci_chunk(int co_tile);
+bool conv_supported(int k, int dil);
+// fp32 CUDA-core fused conv (conv1d.cuh); p.w must be packed with pack_weights(conv_co_tile(Cout), conv_ci_chunk(..)).
+int launch_conv(const ConvParams& p, int k, int dil, int co_tile, bool emb, cudaStream_t st);
+
+}  // namespace dissc

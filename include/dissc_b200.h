@@ -146,6 +146,56 @@ int dissc_gen_profile(dissc_gen_t* g, const int64_t* code, const float* f0, cons
                       char (*names)[64], float* ms, double* flops, double* bytes, int cap, int* n);
 
 /* ------------------------------------------------------------------ *
+ * Prosody predictors  (model/len_predictor.py, model/pitch_predictor.py, infer.py)
+ * ------------------------------------------------------------------ */
+#define DISSC_PRED_LEN 0        /* LenPredictor         model/len_predictor.py:5-52 */
+#define DISSC_PRED_PITCH_NEW 1  /* PitchPredictor       model/pitch_predictor.py:41-104 */
+#define DISSC_PRED_PITCH_BASE 2 /* PitchPredictorBase   model/pitch_predictor.py:106-176 */
+
+typedef struct dissc_pred dissc_pred_t;
+
+/* Replaces: LenPredictor(n_tokens, n_speakers) / PitchPredictor[Base](n_tokens, n_speakers, ...) + .to(dev) +
+ * load_state_dict(torch.load(dir + 'best_model.pth')) + eval()  (infer.py:68-84).  `weights` are the float tensors of
+ * the reference state dict under their reference names ("cnn1.weight", "bn1.running_var", "token_emb.weight",
+ * "pe.pe", ...); eval-mode BatchNorm is folded into the preceding conv here. */
+int dissc_pred_create(dissc_pred_t** out, int kind, int n_tokens, int n_speakers, const dissc_tensor* weights,
+                      int n_weights, int device);
+void dissc_pred_destroy(dissc_pred_t* g);
+int dissc_pred_workspace_bytes(const dissc_pred_t* g, int B, int L, size_t* bytes);
+
+/* Replaces: len_model(dd_seq, spk_id)  (infer.py:30 -> LenPredictor.forward model/len_predictor.py:35-52), batched:
+ * seq int64 (B,L) deduplicated units, spk int64 (B), lengths int32 (B) valid tokens per row (NULL = L; rows behave like
+ * B=1 calls on the unpadded sequence), norm_mean/norm_std = len_norm_stats.pth (infer.py:72); out fp32 (B,L). */
+int dissc_len_forward(dissc_pred_t* g, const int64_t* seq, const int64_t* spk, const int32_t* lengths, int B, int L,
+                      float norm_mean, float norm_std, float* out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Replaces: PitchPredictor[Base].forward  (model/pitch_predictor.py:72-94 / :145-166): cls, reg fp32 (B,L). */
+int dissc_pitch_forward(dissc_pred_t* g, const int64_t* seq, const int64_t* spk, const int32_t* lengths, int B, int L,
+                        float* cls, float* reg, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: calc_freq  (model/pitch_predictor.py:100-104): out = (cls > 0) * (mean[spk] + reg * std[spk]), or
+ * (cls > 0) * reg when mean == std == NULL (norm=True).  mean/std are DEVICE arrays indexed by speaker id. */
+int dissc_pitch_calc_freq(const float* cls, const float* reg, const int64_t* spk, const float* mean, const float* std,
+                          const int32_t* lengths, int B, int L, float* out, void* stream);
+
+/* Replaces: len_carryover_correction  (infer.py:158-172), batched.  lens fp32 (B,L) -> out int32 (B,L) (0 past the
+ * valid length), totals int32 (B) = sum of the corrected lengths (may be NULL).  Bit-exact: fp32 running sum,
+ * round-half-to-even of clamp(lens, 1). */
+int dissc_len_carryover(const float* lens, const int32_t* lengths, int B, int L, int32_t* out, int32_t* totals,
+                        void* stream);
+
+/* Replaces: seqs[seqs != n_tokens] + dedup_seq  (infer.py:25-27, dataset/utils.py:14-16), batched: dd int64 (B,L)
+ * (padded with pad_token), counts int32 (B,L) run lengths, dd_len int32 (B). */
+int dissc_dedup_units(const int64_t* seq, const int32_t* lengths, int64_t pad_token, int B, int L, int64_t* dd,
+                      int32_t* counts, int32_t* dd_len, void* stream);
+
+/* Replaces: torch.repeat_interleave(dd_seq, lens)  (infer.py:32), batched: out int64 (B,L_out) padded with pad_token,
+ * out_len int32 (B) (clipped to L_out). */
+int dissc_repeat_interleave(const int64_t* dd, const int32_t* counts, const int32_t* dd_len, int64_t pad_token, int B,
+                            int L, int L_out, int64_t* out, int32_t* out_len, void* stream);
+
+/* ------------------------------------------------------------------ *
  * Generic fused layers (exposed for layer-level parity tests)
  * ------------------------------------------------------------------ */
 

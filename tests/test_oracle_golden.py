@@ -83,3 +83,34 @@ def test_len_carryover_oracle_matches_reference():
         assert np.array_equal(got, g[f"out{i}"].astype(np.int32)), i
         i += 1
     assert i == 6
+
+
+def test_predictor_oracle_matches_reference():
+    """oracle/predictors_oracle.py vs outputs of the real LenPredictor / PitchPredictor / PitchPredictorBase."""
+    from oracle import predictors_oracle as po
+    g = load_golden("predictors.npz")
+    sd = syn.synthetic_len_predictor_state_dict(100, 108, seed=21)
+    assert syn.state_dict_checksum({k: v for k, v in sd.items()}) == pytest.approx(float(g["len.checksum"]), rel=1e-12)
+    y = po.len_predictor_forward(sd, torch.from_numpy(g["len.seq"]), torch.from_numpy(g["len.spk"]), torch.tensor(2.5),
+                                 torch.tensor(1.5))
+    assert np.abs(y.numpy() - g["len.y"]).max() < 1e-5
+    mean, std = syn.synthetic_pitch_stats(108, seed=22)
+    seq, spk = torch.from_numpy(g["pitch.seq"]), torch.from_numpy(g["pitch.spk"])
+    for tag, kind in (("pitch_new", "new"), ("pitch_base", "base")):
+        sd = syn.synthetic_pitch_predictor_state_dict(kind, 100, 108, seed=23)
+        assert syn.state_dict_checksum(sd) == pytest.approx(float(g[f"{tag}.checksum"]), rel=1e-12)
+        c, r = po.pitch_predictor_forward(sd, seq, spk, kind)
+        assert np.abs(c.numpy() - g[f"{tag}.class"]).max() < 1e-5
+        assert np.abs(r.numpy() - g[f"{tag}.reg"]).max() < 1e-5
+        assert np.abs(po.calc_freq(c, r, spk, norm=True).numpy() - g[f"{tag}.freq_norm"]).max() < 1e-5
+        assert np.abs(po.calc_freq(c, r, spk, mean, std, norm=False).numpy() - g[f"{tag}.freq_hz"]).max() < 2e-3
+
+
+def test_len_carryover_numpy_oracle_matches_reference():
+    from oracle import predictors_oracle as po
+    g = load_golden("len_carryover.npz")
+    i = 0
+    while f"in{i}" in g:
+        assert np.array_equal(po.len_carryover_correction(g[f"in{i}"]), g[f"out{i}"].astype(np.int64)), i
+        i += 1
+    assert i == 6
