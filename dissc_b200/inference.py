@@ -1,0 +1,275 @@
+"""Vocoder CLI -- the host side of the reference's ``sr/inference.py`` on B200.
+
+Same flags, ``config.json`` + newest ``g_*`` checkpoint discovery, manifest format and output names
+(``<stem>_gen.wav`` resynthesis, ``<stem>_<spkr_id>_gen.wav`` voice conversion; float32 wav, peak-normalised,
+``sampling_rate`` Hz).  What changes is the execution model: the reference spawns ``Pool(8)`` workers that each run
+B=1 forwards (sr/inference.py:288-292,351-359); here there is one process per GPU (``torchrun --nproc-per-node N -m
+dissc_b200.inference ...`` or a single process), utterances are length-sorted, dealt to ranks, and vocoded in padded
+batches with per-utterance ``lengths`` -- each row equals the reference's B=1 output for that utterance.
+
+The input side keeps only what feeds the Generator (sr/dataset.py:107-122,291-312): units, F0 (speaker-normalised on
+voiced frames iff ``f0_normalize``) and the speaker id.  The reference additionally loads every ground-truth wav and
+computes a mel-spectrogram per item that inference never uses (sr/dataset.py:224-234,269-271) -- not done here, so no
+``_gt.wav`` copies are written.
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import glob
+import json
+import os
+import pickle
+import random
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .models import AttrDict, CodeGenerator
+
+
+def scan_checkpoint(cp_dir: str, prefix: str) -> str:
+    """sr/inference.py:59-64: newest ``<prefix>*`` by sorted name ('' if none)."""
+    cp_list = glob.glob(os.path.join(cp_dir, prefix + "*"))
+    return sorted(cp_list)[-1] if cp_list else ""
+
+
+def load_config(checkpoint_file: str) -> AttrDict:
+    """sr/inference.py:105-112: config.json next to the checkpoint (file) or inside it (dir)."""
+    d = checkpoint_file if os.path.isdir(checkpoint_file) else os.path.split(checkpoint_file)[0]
+    with open(os.path.join(d, "config.json")) as f:
+        return AttrDict(json.loads(f.read()))
+
+
+def parse_manifest(manifest: str, base_path: str):
+    """sr/dataset.py:107-122 (dict lines are parsed with json / literal_eval instead of eval)."""
+    audio_files, codes, pitch = [], [], []
+    with open(manifest) as info:
+        for line in info.readlines():
+            if line[:1] == "{":
+                try:
+                    sample = json.loads(line.strip())
+                except json.JSONDecodeError:
+                    sample = ast.literal_eval(line.strip())
+                codes.append(np.asarray(sample["units"], dtype=np.int64))
+                audio_files.append(Path(str(base_path) + "/" + sample["audio"].split("/")[-1]))
+                if "f0" in sample:
+                    pitch.append(np.array(sample["f0"]))
+            elif line.strip():
+                audio_files.append(Path(line.strip()))
+    return audio_files, codes, pitch
+
+
+def parse_speaker(path, method) -> str:
+    """sr/dataset.py:132-146."""
+    path = Path(path)
+    if method == "parent_name":
+        return path.parent.name
+    if method == "parent_parent_name":
+        return path.parent.parent.name
+    if method == "_":
+        return path.name.split("_")[0]
+    if method == "single":
+        return "A"
+    if callable(method):
+        return method(path)
+    raise NotImplementedError(method)
+
+
+def normalize_f0(f0: np.ndarray, mean: float, std: float) -> np.ndarray:
+    """sr/dataset.py:306-312 (no f0_median): voiced frames (f0 != 0) -> (f0 - mean) / std; unvoiced stay 0."""
+    f0 = f0.astype(np.float32).copy()
+    ii = f0 != 0
+    f0[ii] = (f0[ii] - mean) / std
+    return f0
+
+
+def prepare_items(h, audio_files, codes, pitch, id_to_spkr: Sequence[str], f0_stats: Optional[dict],
+                  unseen_speaker: bool = False) -> List[dict]:
+    """The slice of CodeDataset.__getitem__ (sr/dataset.py:221-317) that feeds the Generator at inference."""
+    if h.get("f0_median", False) or h.get("f0_feats", False):
+        raise NotImplementedError("f0_median / f0_feats configs are not supported")
+    spkr_to_id = {k: v for v, k in enumerate(id_to_spkr)}
+    items = []
+    for i, (path, code) in enumerate(zip(audio_files, codes)):
+        it = {"name": str(path), "code": np.asarray(code, dtype=np.int64)}
+        if h.get("f0", None):
+            if i >= len(pitch) or len(pitch[i]) == 0:
+                raise NotImplementedError(f"{path}: manifest line has no 'f0' (YAAPT extraction is CPU-only, not ported)")
+            f0 = np.asarray(pitch[i], dtype=np.float32)
+            if h.get("f0_normalize", False):
+                name = parse_speaker(path, h.get("multispkr", None))
+                st = f0_stats if name not in f0_stats else f0_stats[name]
+                mean, std = (st["f0_mean"], st["f0_std"]) if name not in f0_stats else (st["mean"], st["std"])
+                f0 = normalize_f0(f0, mean, std)
+            it["f0"] = f0
+            n = min(len(it["code"]), len(f0))
+            if len(it["code"]) != len(f0):
+                if max(len(it["code"]), len(f0)) % n:
+                    raise NotImplementedError("Padding condition signal - misalignment between condition features.")
+        if h.get("multispkr", None):
+            it["spkr"] = 0 if unseen_speaker else spkr_to_id[parse_speaker(path, h.get("multispkr"))]
+        items.append(it)
+    return items
+
+
+def peak_normalize(audio_i16: np.ndarray) -> np.ndarray:
+    """``librosa.util.normalize(audio.astype(np.float32))`` (sr/inference.py:250): divide by max |x| (inf-norm);
+    all-zero (or tiny, < float32 tiny) signals are returned unchanged."""
+    x = audio_i16.astype(np.float32)
+    peak = np.max(np.abs(x)) if x.size else 0.0
+    if peak < np.finfo(np.float32).tiny:
+        return x
+    return x / peak
+
+
+def write_wav(path: str, rate: int, audio: np.ndarray) -> None:
+    from scipy.io.wavfile import write
+    write(path, rate, audio)
+
+
+def batches_by_length(lengths: Sequence[int], max_batch: int, max_frames: int) -> List[List[int]]:
+    """Greedy length-sorted batching: indices sorted by length (desc), cut when the padded batch would exceed
+    ``max_batch`` rows or ``max_frames`` padded frames."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    out, cur = [], []
+    for i in order:
+        L = int(lengths[cur[0]]) if cur else int(lengths[i])
+        if cur and (len(cur) + 1 > max_batch or (len(cur) + 1) * L > max_frames):
+            out.append(cur)
+            cur = []
+        cur.append(i)
+    if cur:
+        out.append(cur)
+    return out
+
+
+@torch.no_grad()
+def vocode_items(generator: CodeGenerator, items: List[dict], device, spkr_override: Optional[int] = None,
+                 max_batch: int = 64, max_frames: int = 64 * 400) -> Dict[int, np.ndarray]:
+    """-> {item index: int16 waveform (hop * n_frames,)}, identical per item to ``generate()`` (sr/inference.py:67-76)."""
+    hop = generator.hop
+    out: Dict[int, np.ndarray] = {}
+    n_frames = []
+    for it in items:
+        T = len(it["code"])
+        if "f0" in it and len(it["f0"]) > T:
+            T = len(it["f0"])
+        n_frames.append(T)
+    for idx in batches_by_length(n_frames, max_batch, max_frames):
+        T = n_frames[idx[0]]
+        B = len(idx)
+        code = torch.zeros((B, T), dtype=torch.int64)
+        f0 = torch.zeros((B, T), dtype=torch.float32)
+        spkr = torch.zeros((B, 1), dtype=torch.int64)
+        lengths = torch.zeros((B,), dtype=torch.int32)
+        for b, i in enumerate(idx):
+            it = items[i]
+            n = n_frames[i]
+            c = torch.from_numpy(it["code"])
+            if len(c) != n:                      # _upsample: nearest-repeat the shorter signal (sr/models.py:158-177)
+                c = c.repeat_interleave(n // len(c))
+            code[b, :n] = c
+            if "f0" in it:
+                f = torch.from_numpy(np.asarray(it["f0"], dtype=np.float32))
+                if len(f) != n:
+                    f = f.repeat_interleave(n // len(f))
+                f0[b, :n] = f
+            spkr[b, 0] = it.get("spkr", 0) if spkr_override is None else spkr_override
+            lengths[b] = n
+        y = generator.generate_int16(code.to(device), f0.to(device) if generator.f0 else None,
+                                     spkr.to(device) if generator.multispkr else None, lengths=lengths.to(device))
+        y = y.cpu().numpy()
+        for b, i in enumerate(idx):
+            out[i] = y[b, :hop * n_frames[i]].copy()
+    return out
+
+
+def build_parser():
+    """sr/inference.py:263-281."""
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--code_file", default=None)
+    ap.add_argument("--input_code_file", default="./datasets/LJSpeech/cpc100/test.txt")
+    ap.add_argument("--data_path", default=None)
+    ap.add_argument("--output_dir", default="generated_files")
+    ap.add_argument("--checkpoint_file", required=True)
+    ap.add_argument("--f0-stats", type=Path)
+    ap.add_argument("--vc", action="store_true")
+    ap.add_argument("--target-speakers", type=str, nargs="+", default=None)
+    ap.add_argument("--pad", default=None, type=int)
+    ap.add_argument("--debug", action="store_true")
+    ap.add_argument("--eval_mode", action="store_false")
+    ap.add_argument("--parts", action="store_true")
+    ap.add_argument("--unseen-f0", type=Path)
+    ap.add_argument("--unseen_speaker", action="store_true")
+    ap.add_argument("--id_to_spkr", default=None)
+    ap.add_argument("--sample_df", default=None)
+    ap.add_argument("-n", type=int, default=2508)
+    ap.add_argument("--batch", type=int, default=64, help="utterances per forward (extension)")
+    return ap
+
+
+def main(argv: Optional[Sequence[str]] = None):
+    a = build_parser().parse_args(argv)
+    for flag in ("code_file", "f0_stats", "unseen_f0", "sample_df"):
+        if getattr(a, flag):
+            raise NotImplementedError(f"--{flag} is not supported by dissc_b200.inference")
+    from . import dist as ddist
+    rank, world, local = ddist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("dissc_b200.inference needs a CUDA device (sm_100a); there is no CPU path")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    h = load_config(a.checkpoint_file)
+    cp_g = scan_checkpoint(a.checkpoint_file, "g_") if os.path.isdir(a.checkpoint_file) else a.checkpoint_file
+    if not cp_g or not os.path.isfile(cp_g):
+        print(f"Didn't find checkpoints for {cp_g}")   # sr/inference.py:307-309
+        return
+    generator = CodeGenerator(h).to(device)
+    generator.load_state_dict(torch.load(cp_g, map_location="cpu")["generator"])
+    generator.eval()
+    generator.remove_weight_norm()
+    base_path = h.test_base_path if a.data_path is None else a.data_path
+    audio_files, codes, pitch = parse_manifest(a.input_code_file, base_path)
+    spk_pkl = a.id_to_spkr if a.unseen_speaker else f"{os.path.dirname(h.input_training_file)}/id_to_spkr.pkl"
+    with open(spk_pkl, "rb") as f:
+        id_to_spkr = pickle.load(f)
+    f0_stats = None
+    if h.get("f0_stats", None):
+        with open(h.f0_stats, "rb") as f:
+            f0_stats = pickle.load(f)
+    items = prepare_items(h, audio_files, codes, pitch, id_to_spkr, f0_stats, a.unseen_speaker)
+    items = items[: a.n + 1]                                   # reference stops after i > n (sr/inference.py:356-358)
+    mine = ddist.shard_by_length([len(it["code"]) for it in items], world)[rank]
+    my_items = [items[i] for i in mine]
+    os.makedirs(a.output_dir, exist_ok=True)
+    spkr_to_id = {k: v for v, k in enumerate(id_to_spkr)}
+
+    def out_name(it):
+        p = Path(it["name"])
+        return "_".join(p.parts[-3:])[:-4] if a.parts else p.stem
+
+    if not a.unseen_speaker:                                   # resynthesis (sr/inference.py:203-207)
+        for i, audio in vocode_items(generator, my_items, device, None, a.batch).items():
+            write_wav(os.path.join(a.output_dir, out_name(my_items[i]) + "_gen.wav"), h.sampling_rate,
+                      peak_normalize(audio))
+    if h.get("multispkr", None) and a.vc:                      # voice conversion (sr/inference.py:209-251)
+        if a.target_speakers is not None:
+            spkrs = [spkr_to_id[s] for s in a.target_speakers]
+        else:
+            random.seed(52 + rank)
+            spkrs = random.sample(range(len(id_to_spkr)), k=min(5, len(id_to_spkr)))
+        for k in spkrs:
+            for i, audio in vocode_items(generator, my_items, device, k, a.batch).items():
+                write_wav(os.path.join(a.output_dir, out_name(my_items[i]) + f"_{k}_gen.wav"), h.sampling_rate,
+                          peak_normalize(audio))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

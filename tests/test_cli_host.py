@@ -1,0 +1,69 @@
+"""CPU tests of the host-side CLI logic (dissc_b200/inference.py, dissc_b200/infer.py): manifest parsing,
+F0 normalisation, checkpoint discovery, batching.  No GPU, no compute calls."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from dissc_b200 import inference as inf
+from dissc_b200 import infer as pinf
+
+
+def test_parse_manifest_dict_and_json_lines(tmp_path):
+    m = tmp_path / "val.txt"
+    m.write_text("{'units': [1, 1, 2], 'f0': [0.0, 110.5, 0], 'audio': 'some/dir/p225_001_mic2.wav'}\n"
+                 + json.dumps({"units": [5], "f0": [99.0], "audio": "p226_002.wav"}) + "\n")
+    files, codes, pitch = inf.parse_manifest(str(m), "/base")
+    assert [str(f) for f in files] == ["/base/p225_001_mic2.wav", "/base/p226_002.wav"]
+    assert codes[0].tolist() == [1, 1, 2] and codes[0].dtype == np.int64
+    assert pitch[0].tolist() == [0.0, 110.5, 0.0]
+    assert pinf.parse_line("{'units': [3], 'audio': 'a'}") == {"units": [3], "audio": "a"}
+
+
+def test_normalize_f0_only_touches_voiced_frames():
+    f0 = np.array([0, 100, 0, 200], dtype=np.float64)
+    out = inf.normalize_f0(f0, 150.0, 50.0)
+    assert out.dtype == np.float32 and out.tolist() == [0.0, -1.0, 0.0, 1.0]
+
+
+def test_prepare_items_speaker_ids_and_stats():
+    h = inf.AttrDict(f0=True, multispkr="_", f0_normalize=True)
+    files = ["/b/p226_001.wav", "/b/p999_002.wav"]
+    codes = [np.array([1, 2]), np.array([3])]
+    pitch = [np.array([0.0, 120.0]), np.array([90.0])]
+    stats = {"p226": {"mean": 100.0, "std": 10.0}, "f0_mean": 80.0, "f0_std": 5.0}
+    items = inf.prepare_items(h, files, codes, pitch, ["p225", "p226", "p999"], stats)
+    assert items[0]["spkr"] == 1 and items[1]["spkr"] == 2
+    assert items[0]["f0"].tolist() == [0.0, 2.0]
+    assert items[1]["f0"].tolist() == [2.0]          # unknown speaker -> global f0_mean / f0_std
+    with pytest.raises(NotImplementedError):
+        inf.prepare_items(inf.AttrDict(f0=True, multispkr="_"), files, codes, [], ["p226", "p999"], None)
+
+
+def test_scan_checkpoint_and_config(tmp_path):
+    for n in ("g_00000010", "g_00000200", "do_00000200"):
+        (tmp_path / n).write_text("x")
+    (tmp_path / "config.json").write_text(json.dumps({"sampling_rate": 16000}))
+    assert os.path.basename(inf.scan_checkpoint(str(tmp_path), "g_")) == "g_00000200"
+    assert inf.scan_checkpoint(str(tmp_path), "zz_") == ""
+    assert inf.load_config(str(tmp_path)).sampling_rate == 16000
+    assert inf.load_config(str(tmp_path / "g_00000010")).sampling_rate == 16000
+
+
+def test_batches_by_length_and_peak_normalize():
+    lens = [10, 300, 299, 5, 120]
+    b = inf.batches_by_length(lens, max_batch=2, max_frames=10_000)
+    assert b == [[1, 2], [4, 0], [3]]
+    b = inf.batches_by_length(lens, max_batch=64, max_frames=600)
+    assert b[0] == [1, 2] and sorted(sum(b, [])) == [0, 1, 2, 3, 4]
+    x = np.array([0, -16384, 8192], dtype=np.int16)
+    assert inf.peak_normalize(x).tolist() == [0.0, -1.0, 0.5]
+    assert inf.peak_normalize(np.zeros(4, np.int16)).tolist() == [0.0] * 4
+
+
+def test_cli_parsers_keep_reference_flags():
+    a = inf.build_parser().parse_args(["--checkpoint_file", "ck", "--vc", "--target-speakers", "p231", "p239"])
+    assert a.eval_mode is True and a.n == 2508 and a.target_speakers == ["p231", "p239"]
+    p = pinf.build_parser().parse_args(["--pred_len", "--pred_pitch", "--vc", "--target_speakers", "p231"])
+    assert p.norm_pitch is True and p.n == 10 and p.f0_model_type == "new" and p.n_tokens == 100
