@@ -29,6 +29,11 @@ class GenCfg(ctypes.Structure):
     ]
 
 
+class HubertCfg(ctypes.Structure):
+    _fields_ = [("n_layers", c_int), ("embed_dim", c_int), ("ffn_dim", c_int), ("n_heads", c_int), ("conv_dim", c_int),
+                ("pos_kernel", c_int), ("pos_groups", c_int), ("n_clusters", c_int)]
+
+
 class Tensor(ctypes.Structure):
     _fields_ = [("name", c_char_p), ("data", POINTER(c_float)), ("numel", c_int64)]
 
@@ -43,6 +48,8 @@ EXPORTS = [
     "dissc_gen_set_tensor_cores", "dissc_gen_tensor_core_stages", "dissc_conv1d_tc", "dissc_conv_transpose1d_tc", "dissc_tc_set_single_accumulator",
     "dissc_pred_create", "dissc_pred_destroy", "dissc_pred_workspace_bytes", "dissc_len_forward", "dissc_pitch_forward",
     "dissc_pitch_calc_freq", "dissc_len_carryover", "dissc_dedup_units", "dissc_repeat_interleave",
+    "dissc_hubert_create", "dissc_hubert_destroy", "dissc_hubert_num_frames", "dissc_hubert_workspace_bytes",
+    "dissc_hubert_forward", "dissc_kmeans_assign",
 ]
 
 
@@ -99,6 +106,14 @@ def lib():
     L.dissc_dedup_units.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.dissc_repeat_interleave.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                           c_void_p, c_void_p]
+    L.dissc_hubert_create.argtypes = [POINTER(c_void_p), POINTER(HubertCfg), POINTER(Tensor), c_int, c_int]
+    L.dissc_hubert_destroy.argtypes = [c_void_p]
+    L.dissc_hubert_destroy.restype = None
+    L.dissc_hubert_num_frames.argtypes = [c_int]
+    L.dissc_hubert_workspace_bytes.argtypes = [c_void_p, c_int, c_int, POINTER(c_size_t)]
+    L.dissc_hubert_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]
+    L.dissc_kmeans_assign.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     _lib = L
     return L
 

@@ -73,9 +73,19 @@ struct TcParams {
   int up_P;             //   a chunk holds up_P phases x Cout channels, output row = frame*u + phase - up_pad
   int up_pad;
   float div;
-  int plane_act, plain_act;
+  int plane_act, plain_act;  // 0 none, 1 leaky-relu(slope), 2 GELU (erf)
   float plane_slope, plain_slope;
+  int halo;              // zero rows either side of every plane slab (kTcHalo for the vocoder)
+  int pre_act;           // activation applied right after the bias, BEFORE residual / accumulate (0 none, 2 GELU)
+  int out_deint;         // planes output de-interleaved for a following stride-2 conv: row t -> slab phase t&1, row t>>1
+  int groups;            // grouped conv: chunk g reads channel blocks [g*n_cb, (g+1)*n_cb) and writes group_c8 8-channel
+  int group_c8;          //   groups of output channels starting at g*group_c8 (NC >= 8*group_c8, padded columns dropped)
 };
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float tc_act(float v, int mode, float slope) {
+  return mode == 1 ? leaky(v, slope) : (mode == 2 ? gelu_erf(v) : v);
+}
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------------
 // K-major, no swizzle: start address >> 4 | LBO >> 4 (K-chunk stride) << 16 ; high word: SBO (=128 B, stride between
@@ -183,7 +193,11 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
     fence_mbar_init();
   }
   for (int i = tid; i < p.n_chunks * NC; i += kTcThreads) {
-    const int co = p.up ? (i % p.Cout) : i;
+    int co = p.up ? (i % p.Cout) : i;
+    if (p.groups) {
+      const int ch = i / NC, n = i - ch * NC;
+      co = n < p.group_c8 * 8 ? ch * p.group_c8 * 8 + n : p.Cout;
+    }
     s_bias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
   }
   if (warp == 1) {
@@ -207,8 +221,10 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int b = tile / p.tiles_per_b;
         const int r0 = (tile - b * p.tiles_per_b) * 128;
-        const __half* hi0 = p.a_hi + (((size_t)b * p.Cin8) * p.Tp_in + kTcHalo + r0 - p.pad) * 8;
-        const __half* lo0 = p.a_lo + (((size_t)b * p.Cin8) * p.Tp_in + kTcHalo + r0 - p.pad) * 8;
+        const size_t in0 = (((size_t)b * p.Cin8 + (p.groups ? (size_t)chunk * p.n_cb * kb8 : 0)) * p.Tp_in + p.halo + r0 -
+                            p.pad) * 8;
+        const __half* hi0 = p.a_hi + in0;
+        const __half* lo0 = p.a_lo + in0;
         const unsigned char* wchunk = reinterpret_cast<const unsigned char*>(p.w) +
                                       (size_t)chunk * p.n_cb * p.k * w_tap_bytes;
         for (int cb = 0; cb < p.n_cb; ++cb) {
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
       // residual of the first batch: issued before the accumulator wait so its latency hides behind the MMAs
       float4 rq[EB * 2];
       const bool conv_valid = (!p.up) && r < Tvalid;
-      const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * G) * p.Tr + r) * 8;  // conv mode only
+      const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * (p.groups ? p.group_c8 : G)) * p.Tr + r) * 8;  // conv mode
       const size_t fstride = (size_t)p.Tr * 8;
       float4 aq[EB * 2];
       if (p.res && conv_valid) {
@@ -376,12 +392,17 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
             inb = t >= 0 && t < p.T;
             valid = inb && t < Tvalid;
           } else {
-            c8o = n0 >> 3;
+            c8o = p.groups ? chunk * p.group_c8 + g8 : (n0 >> 3);
             t = r;
             inb = true;
             valid = conv_valid;
+            if (p.groups && g8 >= p.group_c8) continue;  // padded output columns of a group
           }
           if (c8o >= cout8) continue;  // padded output columns
+          if (p.pre_act) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tc_act(v[i], p.pre_act, 0.f);
+          }
           const size_t fidx = (((size_t)b * cout8 + c8o) * p.Tr + t) * 8;
           if (valid) {
             if (p.res) {
@@ -410,15 +431,17 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
             if (p.out_plain) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                p.out_plain[((size_t)b * p.Cout + c8o * 8 + i) * p.T + t] = p.plain_act ? leaky(v[i], p.plain_slope) : v[i];
+                p.out_plain[((size_t)b * p.Cout + c8o * 8 + i) * p.T + t] = tc_act(v[i], p.plain_act, p.plain_slope);
             }
           }
           if (p.out_hi && inb) {
             // rows >= valid length are written as zeros: they are the next conv's zero padding
             float a[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = valid ? (p.plane_act ? leaky(v[i], p.plane_slope) : v[i]) : 0.f;
-            const size_t pidx = (((size_t)b * cout8 + c8o) * p.Tp + kTcHalo + t) * 8;
+            for (int i = 0; i < 8; ++i) a[i] = valid ? tc_act(v[i], p.plane_act, p.plane_slope) : 0.f;
+            const size_t pidx = p.out_deint
+                                    ? (((size_t)b * 2 * cout8 + (size_t)(t & 1) * cout8 + c8o) * p.Tp + p.halo + (t >> 1)) * 8
+                                    : (((size_t)b * cout8 + c8o) * p.Tp + p.halo + t) * 8;
             split_store8(p.out_hi + pidx, p.out_lo + pidx, a);
           }
         }
@@ -448,13 +471,13 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
 
 // Zero rows [0,HP) and [HP+T, Tp) of every (b, c8) slab of a plane pair: the conv zero padding
 // (left halo, the round-up rows [T,Tr) and the right halo).
-__global__ void tc_zero_halos_kernel(__half* hi, __half* lo, int slabs, int Tp, int T) {
-  const int per = kTcHalo + (Tp - kTcHalo - T);  // rows per slab to clear
+static __global__ void tc_zero_halos_kernel(__half* hi, __half* lo, int slabs, int Tp, int T, int halo) {
+  const int per = halo + (Tp - halo - T);  // rows per slab to clear
   const long long total = (long long)slabs * per;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(i / per);
     int r = (int)(i - (long long)s * per);
-    r = r < kTcHalo ? r : (T + r);  // second range starts at row HP+T
+    r = r < halo ? r : (T + r);  // second range starts at row halo+T
     const size_t off = ((size_t)s * Tp + r) * 8;
     *reinterpret_cast<uint4*>(hi + off) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(0, 0, 0, 0);
@@ -476,7 +499,7 @@ struct EmbedParams {
   __half* hi;
   __half* lo;
 };
-__global__ void tc_embed_planes_kernel(const EmbedParams p) {
+static __global__ void tc_embed_planes_kernel(const EmbedParams p) {
   const long long total = (long long)p.B * p.C8 * p.Tp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(i % p.Tp);
@@ -506,7 +529,7 @@ __global__ void tc_embed_planes_kernel(const EmbedParams p) {
 
 // plain (B,C,T) fp32 -> split planes [B][C8][Tp][8] (+ optional leaky-relu); rows >= valid length and channels >= C
 // are zero.  Layer-test helper (the model writes planes straight from the producing kernel's epilogue).
-__global__ void tc_pack_planes_kernel(const float* in, __half* hi, __half* lo, const int* lengths, int len_mul, int B, int C,
+static __global__ void tc_pack_planes_kernel(const float* in, __half* hi, __half* lo, const int* lengths, int len_mul, int B, int C,
                                       int C8, int T, int Tp, int act, float slope) {
   const long long total = (long long)B * C8 * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -527,7 +550,7 @@ __global__ void tc_pack_planes_kernel(const float* in, __half* hi, __half* lo, c
 }
 
 // plain (B,C,T) fp32 <-> blocked f32b [B][C/8][Tr][8] (layer-test helpers)
-__global__ void tc_plain_to_f32b_kernel(const float* in, float* out, int B, int C, int T, int Tr) {
+static __global__ void tc_plain_to_f32b_kernel(const float* in, float* out, int B, int C, int T, int Tr) {
   const long long total = (long long)B * C * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % T);
@@ -536,7 +559,7 @@ __global__ void tc_plain_to_f32b_kernel(const float* in, float* out, int B, int 
     out[(((size_t)b * (C / 8) + c / 8) * Tr + t) * 8 + (c & 7)] = in[i];
   }
 }
-__global__ void tc_f32b_to_plain_kernel(const float* in, float* out, int B, int C, int T, int Tr) {
+static __global__ void tc_f32b_to_plain_kernel(const float* in, float* out, int B, int C, int T, int Tr) {
   const long long total = (long long)B * C * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % T);
@@ -546,7 +569,7 @@ __global__ void tc_f32b_to_plain_kernel(const float* in, float* out, int B, int 
   }
 }
 // planes -> plain fp32 (hi + lo), for tests
-__global__ void tc_planes_to_plain_kernel(const __half* hi, const __half* lo, float* out, int B, int C, int T, int Tp) {
+static __global__ void tc_planes_to_plain_kernel(const __half* hi, const __half* lo, float* out, int B, int C, int T, int Tp) {
   const long long total = (long long)B * C * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % T);

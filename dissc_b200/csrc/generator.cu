@@ -23,6 +23,7 @@
 #include "conv_post.cuh"
 #include "convt1d.cuh"
 #include "launch.cuh"
+#include "tc_host.cuh"
 
 namespace dissc {
 
@@ -160,30 +161,21 @@ static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
 // ------------------------------------------------------------------------
 // tensor-core path: plan + weight packing + launch
 // ------------------------------------------------------------------------
-struct TcLayer {
-  bool ok = false;
-  int Cin = 0, Cin_pad = 0, Cout = 0, NC = 0, n_chunks = 1;
-  int k = 0, dil = 1, pad = 0;       // taps / dilation / left padding of the implicit GEMM
-  int up = 0, up_P = 0, up_pad = 0;  // transposed conv: stride, phases per chunk, padding
-  int KB = 0, n_cb = 0, JG = 0, SPC = 0, NS = 0, resident = 0, tmem_cols = 0, acc_cols = 0, nbuf = 1, NA = 2;
-  int single_acc = 0, ctas_per_sm = 1;
-  size_t smem = 0;
-  __half* w = nullptr;  // packed [chunk][cb][tap][KB/8][hi|lo][NC][8], device
-  float inv_scale = 1.f;
-};
-
-constexpr size_t kSmemPerSm = 227 * 1024;
 // NC == 256: one accumulator (so TMEM double-buffers) instead of main+cross.  Measured end to end (profiles/README.md):
 // 1.8e-5 max-abs vs fp64 instead of 7e-6, stage 0 23 % faster.  DISSC_TC_SINGLE_ACC=0 restores the dual accumulator.
 static int g_single_acc256 = -1;
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
-static bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L) {
+bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc) {
   L->ok = false;
-  if (Cin < 1 || taps < 1 || pad > kTcHalo || pad < 0) return false;
-  if ((taps - 1) * dil - pad > kTcHalo) return false;  // right halo
+  if (Cin < 1 || taps < 1 || pad > halo || pad < 0) return false;
+  if ((taps - 1) * dil - pad > halo) return false;  // right halo
   int NC;
-  if (ncols <= 256) {
+  if (force_nc) {
+    if ((force_nc != 16 && force_nc != 32 && force_nc != 64 && force_nc != 128 && force_nc != 256) || ncols % force_nc)
+      return false;
+    NC = force_nc;
+  } else if (ncols <= 256) {
     if (ncols != 16 && ncols != 32 && ncols != 64 && ncols != 128 && ncols != 256) return false;
     NC = ncols;
   } else {
@@ -238,49 +230,9 @@ static bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L) 
   return false;
 }
 
-// Generic packer: wval(n, ci, tap) is the GEMM weight of column n (0 <= n < n_chunks*NC).  Output fp16 hi/lo planes of
-// w*2^s, layout [chunk][cb][tap][KB/8][hi|lo][NC][8].
-template <typename F>
-static std::vector<__half> pack_weights_tc(const TcLayer& L, F wval, float* inv_scale) {
-  const int ncols = L.n_chunks * L.NC;
-  float mx = 0.f;
-  for (int n = 0; n < ncols; ++n)
-    for (int ci = 0; ci < L.Cin; ++ci)
-      for (int j = 0; j < L.k; ++j) mx = std::max(mx, std::fabs(wval(n, ci, j)));
-  int s = 0;
-  if (mx > 0.f) {
-    int e;
-    std::frexp(mx, &e);  // mx = f * 2^e, f in [0.5,1)
-    s = 4 - e;           // mx * 2^s in [8,16)
-    s = std::max(-14, std::min(24, s));
-  }
-  const float scale = std::ldexp(1.f, s);
-  *inv_scale = std::ldexp(1.f, -s);
-  const int kb8 = L.KB / 8;
-  std::vector<__half> out((size_t)L.n_chunks * L.n_cb * L.k * kb8 * 2 * L.NC * 8);
-  size_t o = 0;
-  for (int ch = 0; ch < L.n_chunks; ++ch)
-    for (int cb = 0; cb < L.n_cb; ++cb)
-      for (int j = 0; j < L.k; ++j)
-        for (int c8 = 0; c8 < kb8; ++c8) {
-          __half* hi = &out[o];
-          __half* lo = hi + (size_t)L.NC * 8;
-          o += (size_t)2 * L.NC * 8;
-          for (int n = 0; n < L.NC; ++n)
-            for (int e = 0; e < 8; ++e) {
-              const int ci = cb * L.KB + c8 * 8 + e;
-              const float v = (ci < L.Cin ? wval(ch * L.NC + n, ci, j) : 0.f) * scale;
-              const __half h = __float2half_rn(v);
-              hi[n * 8 + e] = h;
-              lo[n * 8 + e] = __float2half_rn(v - __half2float(h));
-            }
-        }
-  return out;
-}
-
-static bool tc_plan_conv(int Cin, int Cout, int k, int dil, TcLayer* L) {
+bool tc_plan_conv(int Cin, int Cout, int k, int dil, TcLayer* L) {
   if (Cout % 8) return false;
-  if (!tc_plan(Cin, Cout, k, dil, (k * dil - dil) / 2, L)) return false;
+  if (!tc_plan(Cin, Cout, k, dil, (k * dil - dil) / 2, L, kTcHalo)) return false;
   L->Cout = Cout;
   return true;
 }
@@ -289,13 +241,11 @@ static bool tc_plan_conv(int Cin, int Cout, int k, int dil, TcLayer* L) {
 static bool tc_plan_convt(int Cin, int Cout, int k, int u, TcLayer* L) {
   if (Cout % 8 || Cout > 256 || u < 1) return false;
   const int M = (k + u - 1) / u;
-  if (!tc_plan(Cin, u * Cout, M, 1, M - 1, L)) return false;
+  if (!tc_plan(Cin, u * Cout, M, 1, M - 1, L, kTcHalo)) return false;
   if (L->NC % Cout) { L->ok = false; return false; }
   L->Cout = Cout; L->up = u; L->up_P = L->NC / Cout; L->up_pad = (k - u) / 2;
   return true;
 }
-
-static int tc_upload(dissc_gen* g, const std::vector<__half>& packed, __half** out);
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -323,11 +273,13 @@ static int launch_conv_tc_nc(const TcParams& p, const TcLayer& L, int grid, cuda
 
 // p carries the tensors, B, T (output rows), Tr, Tp, Tp_in, lengths and the epilogue switches; `rows` is the number of
 // GEMM rows per utterance (output time steps for a conv, input frames for a transposed conv).
-static int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
+int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
+  if (p.halo == 0) p.halo = kTcHalo;
+  if (L.groups) { p.groups = 1; p.group_c8 = L.group_c8; }
   p.k = L.k; p.dil = L.dil; p.pad = L.pad; p.KB = L.KB; p.n_cb = L.n_cb; p.JG = L.JG; p.SPC = L.SPC; p.NS = L.NS;
   p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.acc_cols = L.acc_cols; p.nbuf = L.nbuf; p.NA = L.NA;
   p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale;
-  p.Cin8 = L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
+  p.Cin8 = L.cin8_total ? L.cin8_total : L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
   p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
   p.tiles_per_b = (rows + 127) / 128;
   p.n_items = p.B * p.tiles_per_b * L.n_chunks;
@@ -342,10 +294,10 @@ static int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t s
   return set_err(DISSC_EINVAL, "bad tensor-core chunk width %d", L.NC);
 }
 
-static int launch_zero_halos(__half* hi, __half* lo, int slabs, int Tp, int T, cudaStream_t st) {
+int launch_zero_halos(__half* hi, __half* lo, int slabs, int Tp, int T, cudaStream_t st, int halo) {
   const long long total = (long long)slabs * (Tp - T);
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  tc_zero_halos_kernel<<<std::max(blocks, 1), 256, 0, st>>>(hi, lo, slabs, Tp, T);
+  tc_zero_halos_kernel<<<std::max(blocks, 1), 256, 0, st>>>(hi, lo, slabs, Tp, T, halo);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }

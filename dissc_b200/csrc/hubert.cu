@@ -1,0 +1,823 @@
+// HuBERT-base unit encoder on the GPU (include/dissc_b200.h, "Unit encoder").
+//
+// Replaces textless `SpeechEncoder.forward` as called at data/encode.py:21-22,32: HuBERT-base (fairseq
+// hubert_base_ls960) features at transformer layer 6 -> nearest of K k-means centroids.  The arithmetic is third-party
+// (textlesslib / fairseq@dd106d95, absent from the reference tree -- SURVEY.md 8c), restated here from the published
+// architecture (fairseq models/hubert/hubert.py + models/wav2vec/wav2vec2.py, extractor mode "default", post-LN
+// encoder); oracle/hubert_oracle.py is the CPU restatement and is cross-checked against torchaudio.models.hubert_base.
+//
+//   wave (B,N) fp32
+//   conv0   Conv1d(1->512,k10,s5,no bias) -> GroupNorm(512,512) over time -> GELU      CUDA cores, 2 passes (stats, apply)
+//   conv1-6 Conv1d(512->512,k3|2,s2,no bias) -> GELU                                   tcgen05 (conv_tc.cuh): the producer
+//           writes its output de-interleaved (even / odd time steps as two channel planes), so a stride-2 conv becomes
+//           a stride-1 implicit GEMM over 1024-channel "frames" with ceil(k/2) taps
+//   LayerNorm(512) -> Linear 512->768                                                  row kernel + tcgen05 (k=1)
+//   x + GELU(pos_conv(x)): Conv1d(768,768,k128,pad64,groups16), last frame dropped     tcgen05 grouped implicit GEMM
+//   LayerNorm(768); 6 x post-LN layer: fused QKV GEMM -> attention (fp32, online softmax) -> out proj + residual -> LN
+//           -> fc1 + GELU -> fc2 + residual -> LN                                      tcgen05 (k=1) + CUDA cores
+//   units = argmin_j ||x - c_j||^2  (first index on ties)                              warp per frame, shuffle reduce
+//
+// All GEMMs use the split-fp16 scheme of conv_tc.cuh (fp32-accurate), so the layer-6 features agree with an fp32
+// evaluation to ~1e-5 and the argmin changes only on near-ties (tests report the margin).
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_host.cuh"
+
+namespace dissc {
+
+constexpr int kHubHalo = 64;  // plane halo rows of the encoder (pos_conv pads 64 frames)
+constexpr int kConv0K = 10, kConv0S = 5, kConv0Chunk = 128;  // frames per CTA in the conv0 kernels
+
+// ---- valid lengths of every extractor layer -----------------------------------------------------------------
+// lens[l*B + b] = frames after conv layer l (l = 0..6) for clip b with n_samples[b] samples
+__global__ void hub_lengths_kernel(const int* n_samples, int N, int B, int* lens) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int n = n_samples ? min(n_samples[b], N) : N;
+  const int ks[7] = {10, 3, 3, 3, 3, 2, 2}, ss[7] = {5, 2, 2, 2, 2, 2, 2};
+  for (int l = 0; l < 7; ++l) {
+    n = n >= ks[l] ? (n - ks[l]) / ss[l] + 1 : 0;
+    lens[l * B + b] = n;
+  }
+}
+
+// ---- conv0 + GroupNorm statistics ----------------------------------------------------------------------------
+// partial[(b*nchunk + chunk)*C + c] = (sum, sumsq) of conv0 output channel c over the chunk's valid frames
+__global__ void __launch_bounds__(256) hub_conv0_stats_kernel(const float* wave, const float* w0, const int* lens0, int N,
+                                                              int C, int nchunk, float2* partial) {
+  __shared__ float sw[kConv0Chunk * kConv0S + kConv0K];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int T0 = lens0[b];
+  const int t0 = chunk * kConv0Chunk;
+  const int nf = max(0, min(kConv0Chunk, T0 - t0));
+  const int ns = nf > 0 ? (nf - 1) * kConv0S + kConv0K : 0;
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) sw[i] = wave[(size_t)b * N + (size_t)t0 * kConv0S + i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float w[kConv0K];
+#pragma unroll
+    for (int j = 0; j < kConv0K; ++j) w[j] = w0[c * kConv0K + j];
+    float s = 0.f, q = 0.f;
+    for (int f = 0; f < nf; ++f) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < kConv0K; ++j) v = fmaf(sw[f * kConv0S + j], w[j], v);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    partial[((size_t)b * nchunk + chunk) * C + c] = make_float2(s, q);
+  }
+}
+
+// scale/shift of GroupNorm(C groups, C channels): y = (x - mean) * rstd * gamma + beta  (biased variance, eps 1e-5)
+__global__ void hub_gn_finalize_kernel(const float2* partial, const float* gamma, const float* beta, const int* lens0,
+                                       int B, int C, int nchunk, float2* scale_shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float2 p = partial[((size_t)b * nchunk + k) * C + c];
+    s += p.x;
+    q += p.y;
+  }
+  const double n = (double)max(lens0[b], 1);
+  const double mean = s / n;
+  const double var = fmax(q / n - mean * mean, 0.0);
+  const double rstd = 1.0 / sqrt(var + 1e-5);
+  const float sc = (float)(rstd * gamma[c]);
+  scale_shift[i] = make_float2(sc, (float)(beta[c] - mean * rstd * gamma[c]));
+}
+
+// conv0 recomputed, normalised, GELU'd and written as split planes, de-interleaved for the stride-2 conv1:
+// out planes [B][2*C/8][Tp][8]: time step t -> slab (t&1)*C/8 + c8, row halo + (t>>1).  Frames >= T0 are zeros.
+__global__ void __launch_bounds__(256) hub_conv0_apply_kernel(const float* wave, const float* w0, const float2* scale_shift,
+                                                              const int* lens0, int N, int C, int Tp, int halo, __half* hi,
+                                                              __half* lo) {
+  extern __shared__ float smem[];
+  float* sw = smem;                                        // wave segment
+  float* sW = sw + kConv0Chunk * kConv0S + kConv0K + 2;    // [C][10]
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int T0 = lens0[b];
+  const int t0 = chunk * kConv0Chunk;
+  const int nf = max(0, min(kConv0Chunk, T0 - t0));
+  const int ns = nf > 0 ? (nf - 1) * kConv0S + kConv0K : 0;
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) sw[i] = wave[(size_t)b * N + (size_t)t0 * kConv0S + i];
+  for (int i = threadIdx.x; i < C * kConv0K; i += blockDim.x) sW[i] = w0[i];
+  __syncthreads();
+  const int c8n = C / 8;
+  // item = (c8, phase, q): lanes run over q so a warp writes 32 consecutive rows of one slab
+  const int qn = kConv0Chunk / 2;
+  for (int item = threadIdx.x; item < c8n * 2 * qn; item += blockDim.x) {
+    const int q = item % qn;
+    const int ph = (item / qn) & 1;
+    const int c8 = item / (2 * qn);
+    const int f = 2 * q + ph;  // frame inside the chunk
+    float v[8];
+    if (f < nf) {
+      float x[kConv0K];
+#pragma unroll
+      for (int j = 0; j < kConv0K; ++j) x[j] = sw[f * kConv0S + j];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = c8 * 8 + e;
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < kConv0K; ++j) a = fmaf(x[j], sW[c * kConv0K + j], a);
+        const float2 ss = scale_shift[(size_t)b * C + c];
+        v[e] = gelu_erf(fmaf(a, ss.x, ss.y));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    }
+    const size_t off = (((size_t)b * 2 * c8n + (size_t)ph * c8n + c8) * Tp + halo + (t0 / 2) + q) * 8;
+    split_store8(hi + off, lo + off, v);
+  }
+}
+
+// ---- LayerNorm over channels, f32b in -> f32b and/or planes out ---------------------------------------------------
+// 8 lanes per row (frame); each lane keeps its 8-channel groups in registers (C <= 768 -> <= 12 groups per lane).
+template <int MAXG>
+__global__ void __launch_bounds__(256) hub_layernorm_kernel(const float* in, const float* gamma, const float* beta,
+                                                            const int* lengths, int B, int C8, int T, int Tr, int Tp,
+                                                            int halo, float* out_f, __half* out_hi, __half* out_lo) {
+  const int sub = threadIdx.x & 7;
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
+  const bool live = row < (long long)B * T;  // no early exit: the 8-lane shuffles below use the full-warp mask
+  if (!live) row = 0;
+  const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+  const bool valid = live && t < (lengths ? min(T, lengths[b]) : T);
+  float x[MAXG][8];
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) {
+    const int c8 = sub + g * 8;
+    if (c8 < C8 && valid) {
+      const float* p = in + (((size_t)b * C8 + c8) * Tr + t) * 8;
+      const float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
+      x[g][0] = a.x; x[g][1] = a.y; x[g][2] = a.z; x[g][3] = a.w;
+      x[g][4] = c.x; x[g][5] = c.y; x[g][6] = c.z; x[g][7] = c.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[g][e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += x[g][e];
+  }
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)(C8 * 8);
+  float q = 0.f;
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) {
+    if (sub + g * 8 < C8) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = x[g][e] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)(C8 * 8) + 1e-5f);
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) {
+    const int c8 = sub + g * 8;
+    if (c8 >= C8 || !live) continue;
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      y[e] = valid ? fmaf((x[g][e] - mean) * rstd, __ldg(gamma + c8 * 8 + e), __ldg(beta + c8 * 8 + e)) : 0.f;
+    if (out_f) {
+      float* p = out_f + (((size_t)b * C8 + c8) * Tr + t) * 8;
+      *reinterpret_cast<float4*>(p) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    if (out_hi) {
+      const size_t off = (((size_t)b * C8 + c8) * Tp + halo + t) * 8;
+      split_store8(out_hi + off, out_lo + off, y);
+    }
+  }
+}
+
+// ---- self-attention (fp32, online softmax) ------------------------------------------------------------------------
+// qkv f32b [B][3*D/8][Tr][8] (q pre-scaled); one thread per query row, 128 rows per CTA, keys/values streamed through
+// shared memory in tiles of 32; out: planes [B][D/8][Tp][8].  Head size 64.
+constexpr int kAttnKT = 32;
+__global__ void __launch_bounds__(128) hub_attention_kernel(const float* qkv, const int* lengths, int D8, int T, int Tr,
+                                                            int Tp, int halo, __half* out_hi, __half* out_lo) {
+  __shared__ __align__(16) float sK[kAttnKT][64];
+  __shared__ __align__(16) float sV[kAttnKT][64];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const int Tv = lengths ? min(T, lengths[b]) : T;
+  const bool active = t < Tv;
+  const size_t bq = (size_t)b * 3 * D8;
+  float q[64], o[64];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 a = make_float4(0, 0, 0, 0), d = a;
+    if (active) {
+      const float* p = qkv + ((bq + h * 8 + c) * Tr + t) * 8;
+      a = *reinterpret_cast<const float4*>(p);
+      d = *reinterpret_cast<const float4*>(p + 4);
+    }
+    q[c * 8 + 0] = a.x; q[c * 8 + 1] = a.y; q[c * 8 + 2] = a.z; q[c * 8 + 3] = a.w;
+    q[c * 8 + 4] = d.x; q[c * 8 + 5] = d.y; q[c * 8 + 6] = d.z; q[c * 8 + 7] = d.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < Tv; k0 += kAttnKT) {
+    __syncthreads();
+    // stage K and V tiles: 32 keys x 64 dims each; element (key, c, e) <- f32b[(D8 + h*8 + c)][k0+key][e]
+    for (int i = threadIdx.x; i < kAttnKT * 16; i += 128) {
+      const int key = i & (kAttnKT - 1), c4 = i / kAttnKT;  // c4: 16 float4 per key row
+      const int c = c4 >> 1, half = c4 & 1;
+      float4 kv = make_float4(0, 0, 0, 0), vv = kv;
+      if (k0 + key < Tv) {
+        kv = *reinterpret_cast<const float4*>(qkv + ((bq + D8 + h * 8 + c) * Tr + k0 + key) * 8 + half * 4);
+        vv = *reinterpret_cast<const float4*>(qkv + ((bq + 2 * D8 + h * 8 + c) * Tr + k0 + key) * 8 + half * 4);
+      }
+      *reinterpret_cast<float4*>(&sK[key][c4 * 4]) = kv;
+      *reinterpret_cast<float4*>(&sV[key][c4 * 4]) = vv;
+    }
+    __syncthreads();
+    const int nk = min(kAttnKT, Tv - k0);
+    float s[kAttnKT];
+    float mx = m;
+#pragma unroll
+    for (int j = 0; j < kAttnKT; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < 16; ++d4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&sK[j][d4 * 4]);
+        a = fmaf(q[d4 * 4], kk.x, a);
+        a = fmaf(q[d4 * 4 + 1], kk.y, a);
+        a = fmaf(q[d4 * 4 + 2], kk.z, a);
+        a = fmaf(q[d4 * 4 + 3], kk.w, a);
+      }
+      s[j] = j < nk ? a : -INFINITY;
+      mx = fmaxf(mx, s[j]);
+    }
+    const float alpha = (m == -INFINITY) ? 0.f : expf(m - mx);
+    l *= alpha;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] *= alpha;
+#pragma unroll
+    for (int j = 0; j < kAttnKT; ++j) {
+      const float pj = (j < nk) ? expf(s[j] - mx) : 0.f;
+      l += pj;
+#pragma unroll
+      for (int d4 = 0; d4 < 16; ++d4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&sV[j][d4 * 4]);
+        o[d4 * 4] = fmaf(pj, vv.x, o[d4 * 4]);
+        o[d4 * 4 + 1] = fmaf(pj, vv.y, o[d4 * 4 + 1]);
+        o[d4 * 4 + 2] = fmaf(pj, vv.z, o[d4 * 4 + 2]);
+        o[d4 * 4 + 3] = fmaf(pj, vv.w, o[d4 * 4 + 3]);
+      }
+    }
+    m = mx;
+  }
+  if (t < T) {
+    const float inv = (active && l > 0.f) ? 1.f / l : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = o[c * 8 + e] * inv;
+      const size_t off = (((size_t)b * D8 + h * 8 + c) * Tp + halo + t) * 8;
+      split_store8(out_hi + off, out_lo + off, y);
+    }
+  }
+}
+
+// ---- k-means assignment ----------------------------------------------------------------------------------------------
+// one warp per frame; x f32b [B][D8][Tr][8]; centroids (K, D) row-major; units int64 (B, T) (-1 past the valid length)
+__global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, const float* cent, const int* lengths, int B,
+                                                              int D8, int T, int Tr, int K, long long* units,
+                                                              float* feat_out /* (B,T,D) or null */) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)B * T) return;
+  const int b = (int)(wid / T), t = (int)(wid - (long long)b * T);
+  const bool valid = t < (lengths ? min(T, lengths[b]) : T);
+  if (!valid) {
+    if (lane == 0) units[wid] = -1;
+    if (feat_out)
+      for (int i = lane; i < D8 * 8; i += 32) feat_out[wid * D8 * 8 + i] = 0.f;
+    return;
+  }
+  float v[4][8];  // D8 <= 128
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c8 = lane + g * 32;
+    if (c8 < D8) {
+      const float* p = x + (((size_t)b * D8 + c8) * Tr + t) * 8;
+      const float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
+      v[g][0] = a.x; v[g][1] = a.y; v[g][2] = a.z; v[g][3] = a.w;
+      v[g][4] = c.x; v[g][5] = c.y; v[g][6] = c.z; v[g][7] = c.w;
+      if (feat_out) {
+        float* f = feat_out + wid * D8 * 8 + c8 * 8;
+        *reinterpret_cast<float4*>(f) = a;
+        *reinterpret_cast<float4*>(f + 4) = c;
+      }
+    }
+  }
+  float best = INFINITY;
+  int besti = 0;
+  for (int j = 0; j < K; ++j) {
+    float d = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c8 = lane + g * 32;
+      if (c8 < D8) {
+        const float* c = cent + (size_t)j * D8 * 8 + c8 * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(c)), e = __ldg(reinterpret_cast<const float4*>(c + 4));
+        float u;
+        u = v[g][0] - a.x; d = fmaf(u, u, d);
+        u = v[g][1] - a.y; d = fmaf(u, u, d);
+        u = v[g][2] - a.z; d = fmaf(u, u, d);
+        u = v[g][3] - a.w; d = fmaf(u, u, d);
+        u = v[g][4] - e.x; d = fmaf(u, u, d);
+        u = v[g][5] - e.y; d = fmaf(u, u, d);
+        u = v[g][6] - e.z; d = fmaf(u, u, d);
+        u = v[g][7] - e.w; d = fmaf(u, u, d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (d < best) {  // strict: first index wins ties (argmin semantics)
+      best = d;
+      besti = j;
+    }
+  }
+  if (lane == 0) units[wid] = besti;
+}
+
+// standalone: x (M, D) row-major
+__global__ void __launch_bounds__(256) kmeans_rowmajor_kernel(const float* x, const float* cent, int M, int D, int K,
+                                                              long long* out) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= M) return;
+  float best = INFINITY;
+  int besti = 0;
+  for (int j = 0; j < K; ++j) {
+    float d = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float u = x[wid * D + i] - __ldg(cent + (size_t)j * D + i);
+      d = fmaf(u, u, d);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (d < best) {
+      best = d;
+      besti = j;
+    }
+  }
+  if (lane == 0) out[wid] = besti;
+}
+
+}  // namespace dissc
+
+using namespace dissc;
+
+struct HubLayer {
+  TcLayer qkv, out, fc1, fc2;
+  float *qkv_b = nullptr, *out_b = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+};
+
+struct dissc_hubert {
+  dissc_hubert_cfg cfg;
+  int device = 0;
+  std::vector<void*> allocs;
+  float *w0 = nullptr, *gn_w = nullptr, *gn_b = nullptr;
+  TcLayer conv[6];
+  float *ln0_w = nullptr, *ln0_b = nullptr;
+  TcLayer proj, pos;
+  float *proj_b = nullptr, *pos_b = nullptr, *eln_w = nullptr, *eln_b = nullptr;
+  std::vector<HubLayer> layers;
+  float* cent = nullptr;
+};
+
+namespace dissc {
+
+struct HubWeights {
+  std::map<std::string, const dissc_tensor*> m;
+  const dissc_tensor* get(const std::string& k) const {
+    auto it = m.find(k);
+    return it == m.end() ? nullptr : it->second;
+  }
+};
+
+static int hub_upload_f(dissc_hubert* g, const float* host, size_t n, float** out) {
+  float* d = nullptr;
+  DISSC_CUDA(cudaMalloc(&d, std::max<size_t>(n, 4) * sizeof(float)));
+  g->allocs.push_back(d);
+  DISSC_CUDA(cudaMemcpy(d, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return DISSC_OK;
+}
+static int hub_upload_h(dissc_hubert* g, const std::vector<__half>& packed, __half** out) {
+  __half* d = nullptr;
+  DISSC_CUDA(cudaMalloc(&d, packed.size() * sizeof(__half)));
+  g->allocs.push_back(d);
+  DISSC_CUDA(cudaMemcpy(d, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  *out = d;
+  return DISSC_OK;
+}
+static int hub_vec(dissc_hubert* g, const HubWeights& wm, const std::string& name, int n, float** out) {
+  const dissc_tensor* t = wm.get(name);
+  DISSC_CHECK(t && t->numel == n, DISSC_EMISSING, "missing tensor %s (%d elements)", name.c_str(), n);
+  return hub_upload_f(g, t->data, n, out);
+}
+// Linear (Cout, Cin) [+ bias] as a k=1 tensor-core conv
+static int hub_linear(dissc_hubert* g, const HubWeights& wm, const std::string& name, int Cin, int Cout, TcLayer* L,
+                      float** bias) {
+  const dissc_tensor* w = wm.get(name + ".weight");
+  DISSC_CHECK(w && w->numel == (int64_t)Cin * Cout, DISSC_EMISSING, "missing tensor %s.weight (%d,%d)", name.c_str(), Cout,
+              Cin);
+  DISSC_CHECK(tc_plan(Cin, Cout, 1, 1, 0, L, kHubHalo), DISSC_EUNSUPPORTED, "%s: no tcgen05 plan for %d->%d", name.c_str(),
+              Cin, Cout);
+  L->Cout = Cout;
+  const float* wd = w->data;
+  auto packed = pack_weights_tc(*L, [=](int n, int ci, int) { return wd[(size_t)n * Cin + ci]; }, &L->inv_scale);
+  int rc = hub_upload_h(g, packed, &L->w);
+  if (rc) return rc;
+  return hub_vec(g, wm, name + ".bias", Cout, bias);
+}
+
+struct Bump {
+  char* base;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 1023) / 1024 * 1024;
+    return p;
+  }
+};
+
+static int conv_out_len(int n, int k, int s) { return n >= k ? (n - k) / s + 1 : 0; }
+
+struct HubShapes {
+  int T[7];   // frames after conv layer l for the longest clip
+  int Tq[6];  // rows of the de-interleaved planes feeding conv l+1: ceil(T[l]/2)
+};
+static HubShapes hub_shapes(int N) {
+  HubShapes s;
+  const int ks[7] = {10, 3, 3, 3, 3, 2, 2}, ss[7] = {5, 2, 2, 2, 2, 2, 2};
+  int n = N;
+  for (int l = 0; l < 7; ++l) {
+    n = conv_out_len(n, ks[l], ss[l]);
+    s.T[l] = n;
+    if (l < 6) s.Tq[l] = (n + 1) / 2;
+  }
+  return s;
+}
+static size_t ru(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct HubBuffers {
+  int* lens;
+  float2* gn_partial;
+  float2* gn_ss;
+  __half* dA[2];  // de-interleaved plane pairs (hi at [0], lo at hi + plane_elems)
+  __half* dB[2];
+  float *X6, *X7, *X8, *H, *Y, *QKV;
+  __half *P6[2], *P7[2], *PH[2], *PA[2], *PF[2];
+  size_t total;
+};
+
+static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
+  const dissc_hubert_cfg& c = g->cfg;
+  const HubShapes s = hub_shapes(N);
+  Bump bp{static_cast<char*>(ws)};
+  HubBuffers b{};
+  const int C = c.conv_dim, D = c.embed_dim;
+  const int nchunk = (std::max(s.T[0], 1) + kConv0Chunk - 1) / kConv0Chunk;
+  b.lens = (int*)bp.take((size_t)7 * B * sizeof(int));
+  b.gn_partial = (float2*)bp.take((size_t)B * nchunk * C * sizeof(float2));
+  b.gn_ss = (float2*)bp.take((size_t)B * C * sizeof(float2));
+  auto plane_bytes = [&](int ch, int rows) { return (size_t)B * (ch / 8) * (ru(std::max(rows, 1), 128) + 2 * kHubHalo) * 16 + 4096; };
+  // ping-pong: dA holds D0, D2, D4; dB holds D1, D3, D5
+  const size_t a_bytes = plane_bytes(2 * C, s.Tq[0]), b_bytes = plane_bytes(2 * C, s.Tq[1]);
+  b.dA[0] = (__half*)bp.take(a_bytes); b.dA[1] = (__half*)bp.take(a_bytes);
+  b.dB[0] = (__half*)bp.take(b_bytes); b.dB[1] = (__half*)bp.take(b_bytes);
+  const int T = std::max(s.T[6], 1);
+  const size_t Tr = ru(T, 128);
+  auto f32b_bytes = [&](int ch) { return (size_t)B * (ch / 8) * Tr * 32 + 4096; };
+  b.X6 = (float*)bp.take(f32b_bytes(C));
+  b.X7 = (float*)bp.take(f32b_bytes(D));
+  b.X8 = (float*)bp.take(f32b_bytes(D));
+  b.H = (float*)bp.take(f32b_bytes(D));
+  b.Y = (float*)bp.take(f32b_bytes(D));
+  b.QKV = (float*)bp.take(f32b_bytes(3 * D));
+  for (int i = 0; i < 2; ++i) {
+    b.P6[i] = (__half*)bp.take(plane_bytes(C, T));
+    b.P7[i] = (__half*)bp.take(plane_bytes(D, T));
+    b.PH[i] = (__half*)bp.take(plane_bytes(D, T));
+    b.PA[i] = (__half*)bp.take(plane_bytes(D, T));
+    b.PF[i] = (__half*)bp.take(plane_bytes(c.ffn_dim, T));
+  }
+  b.total = bp.off;
+  return b;
+}
+
+static int hub_layernorm(const float* in, const float* gw, const float* gb, const int* lengths, int B, int C, int T, int Tr,
+                         int Tp, float* out_f, __half* out_hi, __half* out_lo, cudaStream_t st) {
+  const long long threads = (long long)B * T * 8;
+  const int blocks = (int)((threads + 255) / 256);
+  if (C / 8 <= 64)
+    hub_layernorm_kernel<8><<<blocks, 256, 0, st>>>(in, gw, gb, lengths, B, C / 8, T, Tr, Tp, kHubHalo, out_f, out_hi, out_lo);
+  else
+    hub_layernorm_kernel<12><<<blocks, 256, 0, st>>>(in, gw, gb, lengths, B, C / 8, T, Tr, Tp, kHubHalo, out_f, out_hi, out_lo);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+}  // namespace dissc
+
+#define HUB_TRY(expr)                \
+  do {                               \
+    int _rc = (expr);                \
+    if (_rc != DISSC_OK) return _rc; \
+  } while (0)
+
+extern "C" {
+
+int dissc_hubert_num_frames(int n_samples) { return hub_shapes(n_samples).T[6]; }
+
+int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const dissc_tensor* weights, int n_weights,
+                        int device) {
+  DISSC_CHECK(out && cfg && weights, DISSC_EINVAL, "null argument");
+  *out = nullptr;
+  const dissc_hubert_cfg& c = *cfg;
+  DISSC_CHECK(c.conv_dim == 512 && c.embed_dim % 256 == 0 && c.embed_dim <= 1024 && c.ffn_dim % 256 == 0 &&
+                  c.n_heads * 64 == c.embed_dim && c.n_layers >= 0 && c.pos_groups > 0 &&
+                  c.embed_dim % c.pos_groups == 0 && (c.embed_dim / c.pos_groups) % 16 == 0 &&
+                  c.embed_dim / c.pos_groups <= 64 && c.pos_kernel % 2 == 0 && c.pos_kernel / 2 <= kHubHalo &&
+                  c.n_clusters > 0,
+              DISSC_EUNSUPPORTED,
+              "unsupported HuBERT geometry (need conv_dim 512, head size 64, embed/ffn multiples of 256, pos_conv group "
+              "width a multiple of 16 and <= 64, even pos kernel <= 128)");
+  DISSC_CUDA(cudaSetDevice(device));
+  HubWeights wm;
+  for (int i = 0; i < n_weights; ++i) wm.m[weights[i].name] = &weights[i];
+  dissc_hubert* g = new dissc_hubert();
+  g->cfg = c;
+  g->device = device;
+  auto fail = [&](int rc) {
+    dissc_hubert_destroy(g);
+    return rc;
+  };
+  int rc;
+  const int C = c.conv_dim, D = c.embed_dim;
+  const std::string fe = "feature_extractor.conv_layers.";
+  if ((rc = hub_vec(g, wm, fe + "0.0.weight", C * kConv0K, &g->w0))) return fail(rc);
+  if ((rc = hub_vec(g, wm, fe + "0.2.weight", C, &g->gn_w))) return fail(rc);
+  if ((rc = hub_vec(g, wm, fe + "0.2.bias", C, &g->gn_b))) return fail(rc);
+  for (int l = 1; l <= 6; ++l) {
+    const int k = l <= 4 ? 3 : 2;
+    const dissc_tensor* w = wm.get(fe + std::to_string(l) + ".0.weight");
+    if (!w || w->numel != (int64_t)C * C * k) return fail(set_err(DISSC_EMISSING, "missing %s%d.0.weight (%d,%d,%d)", fe.c_str(), l, C, C, k));
+    TcLayer* L = &g->conv[l - 1];
+    const int taps = (k + 1) / 2;
+    if (!tc_plan(2 * C, C, taps, 1, 0, L, kHubHalo)) return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for extractor conv %d", l));
+    L->Cout = C;
+    const float* wd = w->data;
+    // frame form of a stride-2 conv: channel ci' = phase*C + ci of frame q is x[ci, 2q + phase]; tap j' reads frame q + j'
+    auto packed = pack_weights_tc(*L, [=](int n, int cip, int jp) {
+      const int phase = cip / C, ci = cip % C;
+      const int jj = 2 * jp + phase;
+      return jj < k ? wd[((size_t)n * C + ci) * k + jj] : 0.f;
+    }, &L->inv_scale);
+    if ((rc = hub_upload_h(g, packed, &L->w))) return fail(rc);
+  }
+  if ((rc = hub_vec(g, wm, "layer_norm.weight", C, &g->ln0_w))) return fail(rc);
+  if ((rc = hub_vec(g, wm, "layer_norm.bias", C, &g->ln0_b))) return fail(rc);
+  if ((rc = hub_linear(g, wm, "post_extract_proj", C, D, &g->proj, &g->proj_b))) return fail(rc);
+  {
+    // pos_conv: (D, D/groups, k) folded weight; grouped implicit GEMM, one N-chunk per group
+    const int gw = D / c.pos_groups, k = c.pos_kernel;
+    const dissc_tensor* w = wm.get("encoder.pos_conv.0.weight");
+    if (!w || w->numel != (int64_t)D * gw * k) return fail(set_err(DISSC_EMISSING, "missing encoder.pos_conv.0.weight (%d,%d,%d) [weight-norm folded]", D, gw, k));
+    TcLayer* L = &g->pos;
+    const int NCg = gw <= 16 ? 16 : (gw <= 32 ? 32 : 64);
+    if (!tc_plan(gw, c.pos_groups * NCg, k, 1, k / 2, L, kHubHalo, NCg))
+      return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for pos_conv"));
+    L->Cout = D; L->groups = 1; L->group_c8 = gw / 8; L->cin8_total = D / 8;
+    // grouped layers stream per-group weights: never resident across chunks
+    const float* wd = w->data;
+    auto packed = pack_weights_tc(*L, [=](int n, int ci, int j) {
+      const int grp = n / NCg, nn = n % NCg;
+      return nn < gw ? wd[((size_t)(grp * gw + nn) * gw + ci) * k + j] : 0.f;
+    }, &L->inv_scale);
+    if ((rc = hub_upload_h(g, packed, &L->w))) return fail(rc);
+    if ((rc = hub_vec(g, wm, "encoder.pos_conv.0.bias", D, &g->pos_b))) return fail(rc);
+  }
+  if ((rc = hub_vec(g, wm, "encoder.layer_norm.weight", D, &g->eln_w))) return fail(rc);
+  if ((rc = hub_vec(g, wm, "encoder.layer_norm.bias", D, &g->eln_b))) return fail(rc);
+  g->layers.resize(c.n_layers);
+  for (int l = 0; l < c.n_layers; ++l) {
+    HubLayer& Ly = g->layers[l];
+    const std::string p = "encoder.layers." + std::to_string(l) + ".";
+    // fused QKV: rows [q * head_dim^-0.5 ; k ; v]
+    const dissc_tensor *qw = wm.get(p + "self_attn.q_proj.weight"), *kw = wm.get(p + "self_attn.k_proj.weight"),
+                       *vw = wm.get(p + "self_attn.v_proj.weight"), *qb = wm.get(p + "self_attn.q_proj.bias"),
+                       *kb = wm.get(p + "self_attn.k_proj.bias"), *vb = wm.get(p + "self_attn.v_proj.bias");
+    if (!qw || !kw || !vw || !qb || !kb || !vb || qw->numel != (int64_t)D * D || kw->numel != qw->numel ||
+        vw->numel != qw->numel || qb->numel != D || kb->numel != D || vb->numel != D)
+      return fail(set_err(DISSC_EMISSING, "missing %sself_attn.{q,k,v}_proj.{weight,bias}", p.c_str()));
+    if (!tc_plan(D, 3 * D, 1, 1, 0, &Ly.qkv, kHubHalo)) return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for QKV"));
+    Ly.qkv.Cout = 3 * D;
+    const float scaling = 0.125f;  // head_dim 64 ** -0.5 (fairseq MultiheadAttention.scaling)
+    const float *qd = qw->data, *kd = kw->data, *vd = vw->data;
+    auto packed = pack_weights_tc(Ly.qkv, [=](int n, int ci, int) {
+      return n < D ? qd[(size_t)n * D + ci] * scaling : (n < 2 * D ? kd[(size_t)(n - D) * D + ci] : vd[(size_t)(n - 2 * D) * D + ci]);
+    }, &Ly.qkv.inv_scale);
+    if ((rc = hub_upload_h(g, packed, &Ly.qkv.w))) return fail(rc);
+    std::vector<float> bias(3 * D);
+    for (int i = 0; i < D; ++i) {
+      bias[i] = qb->data[i] * scaling;
+      bias[D + i] = kb->data[i];
+      bias[2 * D + i] = vb->data[i];
+    }
+    if ((rc = hub_upload_f(g, bias.data(), bias.size(), &Ly.qkv_b))) return fail(rc);
+    if ((rc = hub_linear(g, wm, p + "self_attn.out_proj", D, D, &Ly.out, &Ly.out_b))) return fail(rc);
+    if ((rc = hub_linear(g, wm, p + "fc1", D, c.ffn_dim, &Ly.fc1, &Ly.fc1_b))) return fail(rc);
+    if ((rc = hub_linear(g, wm, p + "fc2", c.ffn_dim, D, &Ly.fc2, &Ly.fc2_b))) return fail(rc);
+    if ((rc = hub_vec(g, wm, p + "self_attn_layer_norm.weight", D, &Ly.ln1_w))) return fail(rc);
+    if ((rc = hub_vec(g, wm, p + "self_attn_layer_norm.bias", D, &Ly.ln1_b))) return fail(rc);
+    if ((rc = hub_vec(g, wm, p + "final_layer_norm.weight", D, &Ly.ln2_w))) return fail(rc);
+    if ((rc = hub_vec(g, wm, p + "final_layer_norm.bias", D, &Ly.ln2_b))) return fail(rc);
+  }
+  if ((rc = hub_vec(g, wm, "kmeans.cluster_centers", c.n_clusters * D, &g->cent))) return fail(rc);
+  *out = g;
+  return DISSC_OK;
+}
+
+void dissc_hubert_destroy(dissc_hubert_t* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  for (void* p : g->allocs) cudaFree(p);
+  delete g;
+}
+
+int dissc_hubert_workspace_bytes(const dissc_hubert_t* g, int B, int N, size_t* bytes) {
+  DISSC_CHECK(g && bytes && B > 0 && N > 0, DISSC_EINVAL, "bad argument");
+  *bytes = hub_layout(g, B, N, nullptr).total;
+  return DISSC_OK;
+}
+
+int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_samples, int B, int N, int64_t* units,
+                         int32_t* n_frames, float* features, void* workspace, size_t workspace_bytes, void* stream) {
+  DISSC_CHECK(g && wave && units && B > 0 && N > 0, DISSC_EINVAL, "bad argument");
+  DISSC_CHECK(B <= 65535, DISSC_EINVAL, "B=%d exceeds the grid limit 65535", B);
+  const HubShapes s = hub_shapes(N);
+  DISSC_CHECK(s.T[6] > 0, DISSC_EINVAL, "clips of %d samples are shorter than the 400-sample receptive field", N);
+  size_t need = 0;
+  dissc_hubert_workspace_bytes(g, B, N, &need);
+  DISSC_CHECK(workspace && workspace_bytes >= need, DISSC_EINVAL, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  int dev = -1;
+  DISSC_CUDA(cudaGetDevice(&dev));
+  DISSC_CHECK(dev == g->device, DISSC_EINVAL, "current device %d != handle device %d", dev, g->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dissc_hubert_cfg& c = g->cfg;
+  const int C = c.conv_dim, D = c.embed_dim;
+  HubBuffers bf = hub_layout(g, B, N, workspace);
+
+  hub_lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(n_samples, N, B, bf.lens);
+  DISSC_CUDA(cudaGetLastError());
+  // conv0 + GroupNorm + GELU -> D0 (de-interleaved planes)
+  {
+    const int T0 = s.T[0];
+    const int nchunk = (T0 + kConv0Chunk - 1) / kConv0Chunk;
+    hub_conv0_stats_kernel<<<dim3(nchunk, B), 256, 0, st>>>(wave, g->w0, bf.lens, N, C, nchunk, bf.gn_partial);
+    DISSC_CUDA(cudaGetLastError());
+    hub_gn_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(bf.gn_partial, g->gn_w, g->gn_b, bf.lens, B, C, nchunk,
+                                                                bf.gn_ss);
+    DISSC_CUDA(cudaGetLastError());
+    const int Tq = s.Tq[0];
+    const int Tp = (int)ru(Tq, 128) + 2 * kHubHalo;
+    HUB_TRY(launch_zero_halos(bf.dA[0], bf.dA[1], B * 2 * C / 8, Tp, Tq, st, kHubHalo));
+    const size_t smem = (size_t)(kConv0Chunk * kConv0S + kConv0K + 2 + C * kConv0K) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      DISSC_CUDA(cudaFuncSetAttribute(hub_conv0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr = true;
+    }
+    // chunks cover every frame up to the rounded-up row count so that rows >= T0 inside [0, Tq) are written as zeros
+    const int nchunk_apply = (2 * Tq + kConv0Chunk - 1) / kConv0Chunk;
+    hub_conv0_apply_kernel<<<dim3(nchunk_apply, B), 256, smem, st>>>(wave, g->w0, bf.gn_ss, bf.lens, N, C, Tp, kHubHalo,
+                                                                     bf.dA[0], bf.dA[1]);
+    DISSC_CUDA(cudaGetLastError());
+  }
+  // conv1..conv6 on the tensor cores
+  __half* cur[2] = {bf.dA[0], bf.dA[1]};
+  __half* nxt[2] = {bf.dB[0], bf.dB[1]};
+  const int T = s.T[6];
+  const int Tr = (int)ru(T, 128), Tp = Tr + 2 * kHubHalo;
+  for (int l = 1; l <= 6; ++l) {
+    const int Tin_q = s.Tq[l - 1], Tout = s.T[l];
+    TcParams p{};
+    p.a_hi = cur[0]; p.a_lo = cur[1];
+    p.lengths = bf.lens + l * B; p.len_mul = 1;
+    p.B = B; p.T = Tout; p.halo = kHubHalo;
+    p.Tp_in = (int)ru(Tin_q, 128) + 2 * kHubHalo;
+    if (l < 6) {
+      const int Tq = s.Tq[l];
+      p.Tp = (int)ru(Tq, 128) + 2 * kHubHalo; p.Tr = (int)ru(Tout, 128);
+      p.out_hi = nxt[0]; p.out_lo = nxt[1]; p.plane_act = 2; p.out_deint = 1;
+      HUB_TRY(launch_zero_halos(nxt[0], nxt[1], B * 2 * C / 8, p.Tp, Tq, st, kHubHalo));
+    } else {
+      p.Tp = Tp; p.Tr = Tr;
+      p.out_f32b = bf.X6; p.pre_act = 2;  // GELU, then LayerNorm below
+    }
+    HUB_TRY(launch_conv_tc(p, g->conv[l - 1], Tout, st));
+    std::swap(cur[0], nxt[0]);
+    std::swap(cur[1], nxt[1]);
+  }
+  const int* lenT = bf.lens + 6 * B;
+  // LayerNorm(512) -> planes; post_extract_proj -> x (f32b + planes)
+  HUB_TRY(launch_zero_halos(bf.P6[0], bf.P6[1], B * C / 8, Tp, T, st, kHubHalo));
+  HUB_TRY(hub_layernorm(bf.X6, g->ln0_w, g->ln0_b, lenT, B, C, T, Tr, Tp, nullptr, bf.P6[0], bf.P6[1], st));
+  auto base = [&]() {
+    TcParams p{};
+    p.lengths = lenT; p.len_mul = 1; p.B = B; p.T = T; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp; p.halo = kHubHalo;
+    return p;
+  };
+  {
+    TcParams p = base();
+    p.a_hi = bf.P6[0]; p.a_lo = bf.P6[1]; p.bias = g->proj_b;
+    p.out_f32b = bf.X7; p.out_hi = bf.P7[0]; p.out_lo = bf.P7[1];
+    HUB_TRY(launch_zero_halos(bf.P7[0], bf.P7[1], B * D / 8, Tp, T, st, kHubHalo));
+    HUB_TRY(launch_conv_tc(p, g->proj, T, st));
+  }
+  {
+    // x + GELU(pos_conv(x) + bias)   (fairseq TransformerEncoder.extract_features: x = x + x_conv)
+    TcParams p = base();
+    p.a_hi = bf.P7[0]; p.a_lo = bf.P7[1]; p.bias = g->pos_b; p.pre_act = 2; p.res = bf.X7; p.out_f32b = bf.X8;
+    HUB_TRY(launch_conv_tc(p, g->pos, T, st));
+  }
+  for (int i = 0; i < 2; ++i) {
+    __half** P = i == 0 ? bf.PH : bf.PA;
+    HUB_TRY(launch_zero_halos(P[0], P[1], B * D / 8, Tp, T, st, kHubHalo));
+  }
+  HUB_TRY(launch_zero_halos(bf.PF[0], bf.PF[1], B * c.ffn_dim / 8, Tp, T, st, kHubHalo));
+  HUB_TRY(hub_layernorm(bf.X8, g->eln_w, g->eln_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
+  for (int l = 0; l < c.n_layers; ++l) {
+    const HubLayer& Ly = g->layers[l];
+    {
+      TcParams p = base();
+      p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = Ly.qkv_b; p.out_f32b = bf.QKV;
+      HUB_TRY(launch_conv_tc(p, Ly.qkv, T, st));
+    }
+    hub_attention_kernel<<<dim3((T + 127) / 128, c.n_heads, B), 128, 0, st>>>(bf.QKV, lenT, D / 8, T, Tr, Tp, kHubHalo,
+                                                                               bf.PA[0], bf.PA[1]);
+    DISSC_CUDA(cudaGetLastError());
+    {
+      TcParams p = base();
+      p.a_hi = bf.PA[0]; p.a_lo = bf.PA[1]; p.bias = Ly.out_b; p.res = bf.H; p.out_f32b = bf.Y;
+      HUB_TRY(launch_conv_tc(p, Ly.out, T, st));
+    }
+    HUB_TRY(hub_layernorm(bf.Y, Ly.ln1_w, Ly.ln1_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
+    {
+      TcParams p = base();
+      p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = Ly.fc1_b; p.out_hi = bf.PF[0]; p.out_lo = bf.PF[1]; p.plane_act = 2;
+      HUB_TRY(launch_conv_tc(p, Ly.fc1, T, st));
+    }
+    {
+      TcParams p = base();
+      p.a_hi = bf.PF[0]; p.a_lo = bf.PF[1]; p.bias = Ly.fc2_b; p.res = bf.H; p.out_f32b = bf.Y;
+      HUB_TRY(launch_conv_tc(p, Ly.fc2, T, st));
+    }
+    HUB_TRY(hub_layernorm(bf.Y, Ly.ln2_w, Ly.ln2_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
+  }
+  {
+    const long long threads = (long long)B * T * 32;
+    hub_kmeans_f32b_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(bf.H, g->cent, lenT, B, D / 8, T, Tr, c.n_clusters,
+                                                                         reinterpret_cast<long long*>(units), features);
+    DISSC_CUDA(cudaGetLastError());
+  }
+  if (n_frames) DISSC_CUDA(cudaMemcpyAsync(n_frames, lenT, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return DISSC_OK;
+}
+
+int dissc_kmeans_assign(const float* x, const float* centroids, int M, int D, int K, int64_t* out, void* stream) {
+  DISSC_CHECK(x && centroids && out && M > 0 && D > 0 && K > 0, DISSC_EINVAL, "bad argument");
+  const long long threads = (long long)M * 32;
+  kmeans_rowmajor_kernel<<<(int)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, centroids, M, D, K, reinterpret_cast<long long*>(out));
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+}  // extern "C"

@@ -196,6 +196,55 @@ int dissc_repeat_interleave(const int64_t* dd, const int32_t* counts, const int3
                             int L, int L_out, int64_t* out, int32_t* out_len, void* stream);
 
 /* ------------------------------------------------------------------ *
+ * Unit encoder: HuBERT-base layer-6 features -> k-means units  (data/encode.py:21-22,32)
+ * ------------------------------------------------------------------ */
+
+/* Geometry of the fairseq HuBERT-base graph (hubert_base_ls960: 7-layer conv extractor (512; k 10,3,3,3,3,2,2;
+ * s 5,2,2,2,2,2,2; mode "default"), embed 768, ffn 3072, 12 heads, pos_conv k128 g16) and of the quantiser. */
+typedef struct {
+  int n_layers;   /* transformer layers to run (output_layer = 6 for the shipped pipeline) */
+  int embed_dim;  /* 768 */
+  int ffn_dim;    /* 3072 */
+  int n_heads;    /* 12 (head size must be 64) */
+  int conv_dim;   /* 512 */
+  int pos_kernel; /* 128 */
+  int pos_groups; /* 16 */
+  int n_clusters; /* k-means vocabulary (100) */
+} dissc_hubert_cfg;
+
+typedef struct dissc_hubert dissc_hubert_t;
+
+/* Replaces: SpeechEncoder.by_name(dense_model_name='hubert-base-ls960', quantizer_model_name='kmeans', vocab_size=100,
+ * deduplicate=False).to(device)  (data/encode.py:21-22).  `weights`: fp32 tensors under the fairseq HuBERT state-dict
+ * names ("feature_extractor.conv_layers.0.0.weight", "feature_extractor.conv_layers.0.2.{weight,bias}" (GroupNorm),
+ * "layer_norm.*", "post_extract_proj.*", "encoder.pos_conv.0.{weight,bias}" with the weight-norm ALREADY FOLDED
+ * (w = g * v / ||v|| over dims 0,1 per tap), "encoder.layer_norm.*", "encoder.layers.{l}.self_attn.{q,k,v,out}_proj.*",
+ * "encoder.layers.{l}.self_attn_layer_norm.*", "encoder.layers.{l}.fc{1,2}.*", "encoder.layers.{l}.final_layer_norm.*")
+ * plus "kmeans.cluster_centers" (n_clusters, embed_dim) = sklearn cluster_centers_ of km.bin. */
+int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const dissc_tensor* weights, int n_weights,
+                        int device);
+void dissc_hubert_destroy(dissc_hubert_t* g);
+
+/* Frames produced for a clip of n_samples samples: the (n-k)/s+1 chain of the 7 convs (= floor((n-400)/320)+1). */
+int dissc_hubert_num_frames(int n_samples);
+int dissc_hubert_workspace_bytes(const dissc_hubert_t* g, int B, int N, size_t* bytes);
+
+/* Replaces: encoder(waveform)  (data/encode.py:32), batched.  DEVICE pointers:
+ *   wave      fp32 (B,N)   16 kHz samples, rows zero-padded to N
+ *   n_samples int32 (B)    valid samples per clip (NULL = N); each row is processed exactly like a B=1 call on the
+ *                          unpadded clip (keys past its last frame are masked in attention, convs see zero padding)
+ *   units     int64 (B,T)  T = dissc_hubert_num_frames(N); -1 past a clip's last frame
+ *   n_frames  int32 (B)    frames per clip (may be NULL)
+ *   features  fp32 (B,T,embed_dim) layer-`n_layers` features ('dense'), may be NULL
+ * Asynchronous on `stream`. */
+int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_samples, int B, int N, int64_t* units,
+                         int32_t* n_frames, float* features, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: KMeansQuantizer.forward  (textless): out[i] = argmin_j ||x[i] - centroids[j]||^2, lowest index on ties.
+ * x fp32 (M,D) row-major, centroids fp32 (K,D), out int64 (M); DEVICE pointers. */
+int dissc_kmeans_assign(const float* x, const float* centroids, int M, int D, int K, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------ *
  * Generic fused layers (exposed for layer-level parity tests)
  * ------------------------------------------------------------------ */
 

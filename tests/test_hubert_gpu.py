@@ -1,0 +1,102 @@
+"""GPU parity of the HuBERT-base unit encoder (through the C ABI) against the CPU oracle (parity unpinned: the oracle
+restates the published fairseq graph and is cross-checked against torchaudio, see tests/test_hubert_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hubert_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    torchaudio = pytest.importorskip("torchaudio")
+    torch.manual_seed(0)
+    model = torchaudio.models.hubert_base().eval()
+    sd = ho.from_torchaudio(model, 6)
+    g = torch.Generator().manual_seed(7)
+    lens = [16000, 9000, 12345, 400]
+    waves = [0.1 * torch.randn(n, generator=g) for n in lens]
+    feats = [ho.extract_features(sd, w.view(1, -1), 6)[0] for w in waves]          # each clip alone, unpadded
+    allf = torch.cat(feats, 0)
+    idx = torch.randperm(allf.shape[0], generator=g)[:100]
+    cent = allf[idx] + 0.02 * torch.randn(100, 768, generator=g)
+    return sd, lens, waves, feats, cent
+
+
+def test_features_and_units_varlen_batch(cuda_device, setup):
+    from dissc_b200.hubert import SpeechEncoder
+    sd, lens, waves, feats, cent = setup
+    enc = SpeechEncoder.from_state_dict(sd, cent).to(cuda_device)
+    N = max(lens)
+    wave = torch.zeros(len(lens), N)
+    for b, w in enumerate(waves):
+        wave[b, :len(w)] = w
+        wave[b, len(w):] = 7.0          # garbage past the valid samples must not matter
+    units, n_frames, dense = enc.encode_batch(wave.to(cuda_device), torch.tensor(lens, dtype=torch.int32))
+    units, n_frames, dense = units.cpu(), n_frames.cpu(), dense.cpu()
+    agree = total = 0
+    worst = 0.0
+    for b, f in enumerate(feats):
+        T = ho.num_frames(lens[b])
+        assert int(n_frames[b]) == T == f.shape[0]
+        err = (dense[b, :T] - f).abs().max().item()
+        worst = max(worst, err)
+        assert torch.all(units[b, T:] == -1) and torch.all(dense[b, T:] == 0)
+        d = ho.kmeans_distances(f.double(), cent.double())
+        want = d.argmin(-1)
+        top2 = d.topk(2, dim=-1, largest=False).values
+        margin = (top2[:, 1] - top2[:, 0]) / top2[:, 1].clamp(min=1e-12)
+        sure = margin > 1e-3                         # near-ties may legitimately flip under ~1e-4 feature noise
+        assert torch.equal(units[b, :T][sure], want[sure]), f"clip {b}: unit mismatch outside near-ties"
+        agree += int((units[b, :T] == want).sum())
+        total += T
+    assert worst < 2e-3, f"layer-6 feature max-abs error {worst}"
+    assert agree / total > 0.98
+    print(f"hubert: feature max-abs err {worst:.2e}; units agree {agree}/{total}")
+
+
+def test_call_surface_matches_data_encode(cuda_device, setup):
+    from dissc_b200.hubert import SpeechEncoder
+    sd, lens, waves, feats, cent = setup
+    enc = SpeechEncoder.from_state_dict(sd, cent, deduplicate=False).to(cuda_device)
+    out = enc(waves[1].view(1, -1).to(cuda_device))            # data/encode.py:32
+    assert set(out) == {"units", "durations", "dense"}
+    T = ho.num_frames(lens[1])
+    assert out["units"].shape == (T,) and out["units"].dtype == torch.int64
+    assert torch.all(out["durations"] == 1) and out["dense"].shape == (T, 768)
+    dd = SpeechEncoder.from_state_dict(sd, cent, deduplicate=True).to(cuda_device)(waves[1].to(cuda_device))
+    assert int(dd["durations"].sum()) == T and torch.equal(torch.repeat_interleave(dd["units"], dd["durations"]), out["units"])
+    # B=1 equals the same clip inside a padded batch
+    wave = torch.zeros(2, lens[0])
+    wave[0], wave[1, :lens[1]] = waves[0], waves[1]
+    u, nf, _ = enc.encode_batch(wave.to(cuda_device), torch.tensor([lens[0], lens[1]], dtype=torch.int32))
+    assert torch.equal(u[1, :T], out["units"])
+
+
+def test_kmeans_assign_exact(cuda_device):
+    from dissc_b200.hubert import kmeans_assign
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 768, generator=g)
+    c = torch.randn(100, 768, generator=g)
+    c[37] = c[5]                                               # exact tie -> lowest index must win
+    x[0] = c[5]
+    got = kmeans_assign(x.to(cuda_device), c).cpu()
+    d = ho.kmeans_distances(x.double(), c.double())
+    top2 = d.topk(2, dim=-1, largest=False).values
+    sure = (top2[:, 1] - top2[:, 0]) > 1e-3
+    assert got[0] == 5
+    assert torch.equal(got[sure], d.argmin(-1)[sure])
+    # small integer-valued data: distances are exact in fp32 -> bit-exact argmin incl. ties
+    xi = torch.randint(-3, 4, (500, 64), generator=g).float()
+    ci = torch.randint(-3, 4, (50, 64), generator=g).float()
+    assert torch.equal(kmeans_assign(xi.to(cuda_device), ci).cpu(), ho.kmeans_assign(xi, ci))
+
+
+def test_short_clip_rejected(cuda_device, setup):
+    from dissc_b200.hubert import SpeechEncoder
+    sd, _, _, _, cent = setup
+    enc = SpeechEncoder.from_state_dict(sd, cent).to(cuda_device)
+    with pytest.raises(ValueError):
+        enc.encode_batch(torch.zeros(1, 399, device=cuda_device))
