@@ -100,3 +100,34 @@ def test_short_clip_rejected(cuda_device, setup):
     enc = SpeechEncoder.from_state_dict(sd, cent).to(cuda_device)
     with pytest.raises(ValueError):
         enc.encode_batch(torch.zeros(1, 399, device=cuda_device))
+
+
+def test_encode_cli_end_to_end(cuda_device, setup, tmp_path):
+    """dissc_b200.encode (data/encode.py surface): wav files -> JSON lines, from fairseq-style checkpoint files."""
+    import json
+    from scipy.io import wavfile
+    from dissc_b200 import encode as enc_cli
+    sd, lens, waves, feats, cent = setup
+    wav_dir = tmp_path / "wav"
+    wav_dir.mkdir()
+    names = []
+    for i, w in enumerate(waves[:3]):
+        pcm = (w.clamp(-1, 1) * 32767).round().to(torch.int16)
+        wavfile.write(wav_dir / f"p225_{i:03d}.wav", 16000, pcm.numpy())
+        names.append(f"p225_{i:03d}.wav")
+    torch.save({"cfg": {"model": "hubert"}, "model": sd}, tmp_path / "hubert.pt")
+    np.save(tmp_path / "km.npy", cent.numpy())
+    out = tmp_path / "hubert100" / "train.txt"
+    enc_cli.main(["--base_dir", str(wav_dir), "--out_file", str(out), "--device", "cuda:0",
+                  "--hubert_checkpoint", str(tmp_path / "hubert.pt"), "--kmeans_path", str(tmp_path / "km.npy")])
+    rows = [json.loads(l) for l in open(out)]
+    assert [r["audio"] for r in rows] == names
+    for r, n in zip(rows, lens[:3]):
+        T = ho.num_frames(n)
+        assert len(r["units"]) == T and r["durations"] == [1] * T and set(r) == {"units", "durations", "audio"}
+        pcm = torch.from_numpy(wavfile.read(wav_dir / r["audio"])[1].astype(np.float32) / 32768.0)
+        f = ho.extract_features(sd, pcm.view(1, -1), 6)[0]
+        d = ho.kmeans_distances(f.double(), cent.double())
+        top2 = d.topk(2, dim=-1, largest=False).values
+        sure = (top2[:, 1] - top2[:, 0]) / top2[:, 1].clamp(min=1e-12) > 1e-3
+        assert torch.equal(torch.tensor(r["units"])[sure], d.argmin(-1)[sure])
