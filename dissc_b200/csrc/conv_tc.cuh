@@ -78,6 +78,8 @@ struct TcParams {
   int halo;              // zero rows either side of every plane slab (kTcHalo for the vocoder)
   int pre_act;           // activation applied right after the bias, BEFORE residual / accumulate (0 none, 2 GELU)
   int out_deint;         // planes output de-interleaved for a following stride-2 conv: row t -> slab phase t&1, row t>>1
+  int f_halo;            // f32b tensors (res / acc_in / out_f32b): rows of slack in front of every slab (0 = plain f32b;
+                         //   > 0 = the "f32h" layout of resblock_tc.cuh, with Tr = rows per slab incl. slack)
   int groups;            // grouped conv: chunk g reads channel blocks [g*n_cb, (g+1)*n_cb) and writes group_c8 8-channel
   int group_c8;          //   groups of output channels starting at g*group_c8 (NC >= 8*group_c8, padded columns dropped)
 };
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
       // residual of the first batch: issued before the accumulator wait so its latency hides behind the MMAs
       float4 rq[EB * 2];
       const bool conv_valid = (!p.up) && r < Tvalid;
-      const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * (p.groups ? p.group_c8 : G)) * p.Tr + r) * 8;  // conv mode
+      const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * (p.groups ? p.group_c8 : G)) * p.Tr + p.f_halo + r) * 8;
       const size_t fstride = (size_t)p.Tr * 8;
       float4 aq[EB * 2];
       if (p.res && conv_valid) {
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = tc_act(v[i], p.pre_act, 0.f);
           }
-          const size_t fidx = (((size_t)b * cout8 + c8o) * p.Tr + t) * 8;
+          const size_t fidx = (((size_t)b * cout8 + c8o) * p.Tr + p.f_halo + t) * 8;
           if (valid) {
             if (p.res) {
               v[0] += rq[2 * e].x; v[1] += rq[2 * e].y; v[2] += rq[2 * e].z; v[3] += rq[2 * e].w;

@@ -24,6 +24,7 @@
 #include "convt1d.cuh"
 #include "launch.cuh"
 #include "tc_host.cuh"
+#include "resblock_tc.cuh"
 
 namespace dissc {
 
@@ -303,6 +304,64 @@ int launch_zero_halos(__half* hi, __half* lo, int slabs, int Tp, int T, cudaStre
 }
 
 // ------------------------------------------------------------------------
+// fused ResBlock pair (resblock_tc.cuh): plan + launch
+// ------------------------------------------------------------------------
+constexpr int kPairHalo = 32;    // f32h: slack rows in front of every slab (>= p1 + p2 = 30 for k=11, d=5)
+constexpr int kPairSlack = 224;  // f32h: Tpf = roundup(T,128) + kPairSlack
+static int g_use_pair = -1;      // DISSC_TC_PAIR=0 disables the fused pair kernel
+
+struct PairLayer {
+  bool ok = false;
+  int C = 0, k = 0, dil = 1, tmem_cols = 0, ctas_per_sm = 1;
+  size_t smem = 0;
+};
+
+static bool pair_plan(int C, int k, int dil, const TcLayer& c1, const TcLayer& c2, PairLayer* L) {
+  L->ok = false;
+  if (g_use_pair < 0) {
+    const char* e = getenv("DISSC_TC_PAIR");
+    g_use_pair = e ? (atoi(e) != 0) : 1;
+  }
+  if (!g_use_pair || (C != 16 && C != 32) || !(k & 1) || k < 1 || k > 33) return false;
+  if (!c1.ok || !c2.ok || c1.n_cb != 1 || c2.n_cb != 1 || c1.NC != C || c2.NC != C || c1.n_chunks != 1) return false;
+  const int p1 = dil * (k - 1) / 2, p2 = (k - 1) / 2;
+  if (p1 + p2 > kPairHalo || 128 - (k - 1) < 64) return false;
+  const size_t R1 = 128 + (size_t)(k - 1) * dil, R2 = 128 + (k - 1), C8 = C / 8;
+  const size_t stg = C8 * R1 * 32, xop = 2 * C8 * R1 * 16, xt = 2 * C8 * R2 * 16, w = (size_t)k * C8 * 2 * C * 16;
+  L->smem = 2 * (stg + xop + xt + w) + 2 * C * 4 + 17 * 8 + 128;
+  if (L->smem > kSmemPerSm - 1536) return false;
+  L->C = C; L->k = k; L->dil = dil;
+  L->tmem_cols = 8 * C;  // two groups x (acc1, acc2) x (main | cross)
+  L->ctas_per_sm = (C == 16) ? (int)std::max<size_t>(1, std::min<size_t>(2, kSmemPerSm / (L->smem + 1536))) : 1;
+  L->ok = true;
+  return true;
+}
+
+template <int NC>
+static int launch_pair_nc(const PairParams& p, const PairLayer& L, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DISSC_CUDA(cudaFuncSetAttribute(resblock_pair_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSmemPerSm - 1024)));
+    attr_set = true;
+  }
+  resblock_pair_tc_kernel<NC><<<grid, kPairThreads, L.smem, st>>>(p);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+static int launch_pair(PairParams p, const PairLayer& L, const TcLayer& c1, const TcLayer& c2, cudaStream_t st) {
+  p.k = L.k; p.dil = L.dil; p.tmem_cols = L.tmem_cols;
+  p.w1 = c1.w; p.w2 = c2.w; p.inv1 = c1.inv_scale; p.inv2 = c2.inv_scale;
+  const int m_out = 128 - (L.k - 1);
+  p.tiles_per_b = (p.T + m_out - 1) / m_out;
+  p.n_tiles = p.B * p.tiles_per_b;
+  const int grid = std::min(p.n_tiles, num_sms() * L.ctas_per_sm);
+  if (L.C == 16) return launch_pair_nc<16>(p, L, grid, st);
+  return launch_pair_nc<32>(p, L, grid, st);
+}
+
+// ------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------
 struct ConvLayer {
@@ -343,6 +402,8 @@ struct dissc_gen {
   // tensor-core twins of rb[][][][] and per-stage eligibility
   TcLayer rb_tc[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS][2];
   bool stage_tc[DISSC_MAX_STAGES] = {};
+  PairLayer rb_pair[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // fused (c1,c2) pairs, narrow stages
+  bool stage_pair[DISSC_MAX_STAGES] = {};
   TcLayer pre_tc, ups_tc[DISSC_MAX_STAGES];  // conv_pre / upsamplers on the tensor cores
   bool tc_all = false;                        // every layer but conv_post has a tcgen05 plan: planes flow end to end
   int use_tc = 1;
@@ -456,7 +517,7 @@ static size_t region_bytes(const dissc_gen* g, int B, int T) {
   for (int i = 0; i < g->cfg.n_up; ++i) {
     const ConvTLayer& U = g->ups[i];
     t = (t - 1) * U.u - 2 * U.pad + U.k;
-    const size_t tp = round_up(t, 128) + 2 * kTcHalo;
+    const size_t tp = round_up(t, 128) + std::max(2 * kTcHalo, kPairSlack);
     mx = std::max(mx, (size_t)B * round_up(U.Cout, 8) * tp * 4);
   }
   return round_up(mx, 1024) + 8192;
@@ -603,13 +664,19 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     const int Tr = (int)round_up(Tout, 128), Tp = Tr + 2 * kTcHalo;
     const int ch = U.Cout;
     const bool last_stage = (i == c.n_up - 1);
+    const bool pair = tc_all && g->stage_pair[i];            // fused (c1,c2) pairs on fp32 "f32h" tensors
+    const int Tpf = Tr + kPairSlack;
     if (tc) {
       // zero padding of the plane pairs this stage writes (halo rows + round-up rows)
       DISSC_TRY(L.begin("zero_halos", 0));
-      DISSC_TRY(launch_zero_halos(P_up.hi, P_up.lo, B * ch / 8, Tp, Tout, st));
-      DISSC_TRY(launch_zero_halos(P_xt.hi, P_xt.lo, B * ch / 8, Tp, Tout, st));
-      DISSC_TRY(launch_zero_halos(P_r.hi, P_r.lo, B * ch / 8, Tp, Tout, st));
-      L.count += 2;
+      if (!pair) {
+        DISSC_TRY(launch_zero_halos(P_up.hi, P_up.lo, B * ch / 8, Tp, Tout, st));
+        DISSC_TRY(launch_zero_halos(P_xt.hi, P_xt.lo, B * ch / 8, Tp, Tout, st));
+        DISSC_TRY(launch_zero_halos(P_r.hi, P_r.lo, B * ch / 8, Tp, Tout, st));
+        L.count += 2;
+      } else if (last_stage) {
+        --L.count;  // nothing to clear: begin() counted a launch that does not happen
+      }
       if (tc_all && !last_stage) {
         DISSC_TRY(launch_zero_halos(P_act[cur ^ 1].hi, P_act[cur ^ 1].lo, B * ch / 8, Tp, Tout, st));
         L.count += 1;
@@ -626,6 +693,9 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
       p.out_f32b = F_up; p.out_hi = P_up.hi; p.out_lo = P_up.lo; p.plane_act = 1; p.plane_slope = 0.1f;
       p.lengths = lengths; p.len_mul = mul * U.u;
       p.B = B; p.T = Tout; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp_in;
+      if (pair) {  // the fused pairs read x as fp32 only
+        p.out_hi = nullptr; p.out_lo = nullptr; p.Tr = Tpf; p.f_halo = kPairHalo;
+      }
       const int n_frames = (Tout + U.pad - 1) / U.u + 1;
       DISSC_TRY(launch_conv_tc(p, g->ups_tc[i], n_frames, st));
     } else {
@@ -653,6 +723,35 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
         const double S = 4.0 * ch * (double)Tcur * B, wb = 4.0 * ch * ch * (double)c1.k;
         const double by1 = 2 * S + wb;                                                       // K3: 1R + 1W
         const double by2 = 3 * S + wb + ((m == c.n_dil - 1 && j > 0) ? S : 0.0);             // K4: 2R + 1W (+ xs read)
+        if (pair) {
+          // K3+K4 fused: x' = x + conv2(lrelu(conv1(lrelu(x))))  [-> MRF accumulate]   (sr/models.py:36-40, :104-109)
+          float* F_rr[2] = {F_r, xt};  // ping-pong (a tile reads halo rows its neighbours write)
+          PairParams q{};
+          q.x = (m == 0) ? F_up : F_rr[(m - 1) & 1];
+          q.b1 = c1.bias; q.b2 = g->rb[i][j][m][1].bias;
+          q.lengths = lengths; q.len_mul = mul;
+          q.B = B; q.T = Tcur; q.Tpf = Tpf; q.f_halo = kPairHalo; q.Tp = Tp; q.p_halo = kTcHalo;
+          if (!last_m) {
+            q.out_f = F_rr[m & 1];
+          } else {
+            if (j > 0) q.acc_in = F_xs;
+            if (!last_j) {
+              q.out_f = F_xs;
+            } else {
+              q.div = (float)c.n_rk;
+              if (!last_stage) {
+                q.out_hi = P_act[cur ^ 1].hi; q.out_lo = P_act[cur ^ 1].lo; q.plane_act = 1; q.plane_slope = next_slope;
+              } else {
+                q.out_plain = xs; q.plain_act = 1; q.plain_slope = next_slope;
+              }
+            }
+          }
+          snprintf(name, sizeof(name), "s%d.rb%d.pair.%d.ptc", i, j, m);
+          DISSC_TRY(L.begin(name, 2 * fl, by1 + by2));
+          DISSC_TRY(launch_pair(q, g->rb_pair[i][j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], st));
+          DISSC_TRY(L.end());
+          continue;
+        }
         if (tc) {
           const Planes rin_p = (m == 0) ? P_up : P_r;
           const float* rin_f = (m == 0) ? F_up : F_r;
@@ -841,6 +940,14 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
         return fail(rc);
       g->tc_all = g->ups_tc[i].ok;
     }
+  }
+  // fused ResBlock pairs for the narrow stages (only inside the all-tensor-core pipeline, ResBlock1 only)
+  for (int i = 0; i < c.n_up; ++i) {
+    g->stage_pair[i] = g->tc_all && c.resblock == 1;
+    for (int j = 0; j < c.n_rk && g->stage_pair[i]; ++j)
+      for (int m = 0; m < c.n_dil && g->stage_pair[i]; ++m)
+        g->stage_pair[i] = pair_plan(c.c0 >> (i + 1), c.rk[j], c.dil[j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1],
+                                     &g->rb_pair[i][j][m]);
   }
   // conv_post: (1, ch, 7) -> plain (ch, 7)
   {
@@ -1207,6 +1314,75 @@ int dissc_conv_transpose1d_tc(const float* in, const float* w_host, const float*
   if (!rc) rc = launch_conv_tc(p, L, n_frames, st);
   if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, Cout, Tout, Tr);
   if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, Cout, Tout, Tp);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cleanup();
+  if (rc) return rc;
+  DISSC_CUDA(e);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+int dissc_resblock_pair_tc(const float* in, const float* w1_host, const float* b1_host, const float* w2_host,
+                           const float* b2_host, const float* acc_in, float* out_raw, float* out_planes,
+                           const int32_t* lengths, int len_mul, int B, int C, int T, int k, int dilation, float div,
+                           float plane_slope, void* stream) {
+  DISSC_CHECK(in && w1_host && w2_host && B > 0 && C > 0 && T > 0, DISSC_EINVAL, "bad argument");
+  TcLayer c1, c2;
+  PairLayer L;
+  DISSC_CHECK(tc_plan_conv(C, C, k, dilation, &c1) && tc_plan_conv(C, C, k, 1, &c2) && pair_plan(C, k, dilation, c1, c2, &L),
+              DISSC_EUNSUPPORTED, "no fused-pair plan for C=%d kernel_size=%d dilation=%d (C in {16,32}, odd k, halo <= %d)",
+              C, k, dilation, kPairHalo);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Tr = (int)round_up(T, 128), Tp = Tr + 2 * kTcHalo, Tpf = Tr + kPairSlack;
+  const size_t f_elems = (size_t)B * (C / 8) * Tpf * 8, plane_elems = (size_t)B * (C / 8) * Tp * 8;
+  auto pk1 = pack_weights_tc(c1, [=](int n, int ci, int j) { return w1_host[((size_t)n * C + ci) * k + j]; }, &c1.inv_scale);
+  auto pk2 = pack_weights_tc(c2, [=](int n, int ci, int j) { return w2_host[((size_t)n * C + ci) * k + j]; }, &c2.inv_scale);
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    tmp.push_back(d);
+    return d;
+  };
+  auto cleanup = [&]() { for (void* d : tmp) cudaFree(d); };
+  __half* dw1 = (__half*)dalloc(pk1.size() * 2);
+  __half* dw2 = (__half*)dalloc(pk2.size() * 2);
+  float* db = (float*)dalloc((size_t)2 * C * 4);
+  float* f_in = (float*)dalloc(f_elems * 4);
+  float* f_acc = (float*)dalloc(f_elems * 4);
+  float* f_out = (float*)dalloc(f_elems * 4);
+  __half* o_hi = (__half*)dalloc(plane_elems * 2);
+  __half* o_lo = (__half*)dalloc(plane_elems * 2);
+  if (!dw1 || !dw2 || !db || !f_in || !f_acc || !f_out || !o_hi || !o_lo) {
+    cleanup();
+    return set_err(DISSC_ENOMEM, "cudaMalloc failed in dissc_resblock_pair_tc");
+  }
+  cudaMemcpyAsync(dw1, pk1.data(), pk1.size() * 2, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dw2, pk2.data(), pk2.size() * 2, cudaMemcpyHostToDevice, st);
+  std::vector<float> bias(2 * C, 0.f);
+  if (b1_host) memcpy(bias.data(), b1_host, C * 4);
+  if (b2_host) memcpy(bias.data() + C, b2_host, C * 4);
+  cudaMemcpyAsync(db, bias.data(), (size_t)2 * C * 4, cudaMemcpyHostToDevice, st);
+  // NaN bit patterns everywhere first: the kernel must not depend on the slack rows or on rows past the valid length
+  cudaMemsetAsync(f_in, 0xff, f_elems * 4, st);
+  cudaMemsetAsync(f_acc, 0xff, f_elems * 4, st);
+  cudaMemsetAsync(f_out, 0xff, f_elems * 4, st);
+  cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
+  const int nb = 148 * 4;
+  tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(in, f_in + (size_t)kPairHalo * 8, B, C, T, Tpf);
+  if (acc_in) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(acc_in, f_acc + (size_t)kPairHalo * 8, B, C, T, Tpf);
+  int rc = launch_zero_halos(o_hi, o_lo, B * C / 8, Tp, T, st);
+  c1.w = dw1; c2.w = dw2;
+  PairParams p{};
+  p.x = f_in; p.b1 = db; p.b2 = db + C; p.acc_in = acc_in ? f_acc : nullptr;
+  p.out_f = f_out; p.out_hi = out_planes ? o_hi : nullptr; p.out_lo = out_planes ? o_lo : nullptr;
+  p.lengths = lengths; p.len_mul = len_mul;
+  p.B = B; p.T = T; p.Tpf = Tpf; p.f_halo = kPairHalo; p.Tp = Tp; p.p_halo = kTcHalo;
+  p.div = div; p.plane_act = 1; p.plane_slope = plane_slope;
+  if (!rc) rc = launch_pair(p, L, c1, c2, st);
+  if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out + (size_t)kPairHalo * 8, out_raw, B, C, T, Tpf);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp);
   cudaError_t e = cudaStreamSynchronize(st);
   cleanup();
   if (rc) return rc;

@@ -278,6 +278,15 @@ int dissc_conv_transpose1d_tc(const float* in, const float* w_host, const float*
                               float* out_planes, const int32_t* lengths, int len_mul, int B, int Cin, int Cout,
                               int T_in, int k, int u, float plane_slope, void* stream);
 
+/* Fused ResBlock1 pair on the tensor cores (C = 16 or 32; sr/models.py:36-40):
+ *   out_raw = [acc_in +] in + conv1d(lrelu(conv1d(lrelu(in, 0.1), w1, dilation), 0.1), w2)   [/ div]
+ *   out_planes = leaky_relu(out_raw, plane_slope) through the fp16 split.
+ * Plain (B,C,T) fp32 DEVICE tensors; weights (C,C,k) / biases (C) on the HOST (test entry, not a fast path). */
+int dissc_resblock_pair_tc(const float* in, const float* w1_host, const float* b1_host, const float* w2_host,
+                           const float* b2_host, const float* acc_in, float* out_raw, float* out_planes,
+                           const int32_t* lengths, int len_mul, int B, int C, int T, int k, int dilation, float div,
+                           float plane_slope, void* stream);
+
 const char* dissc_last_error(void);
 const char* dissc_version(void);
 

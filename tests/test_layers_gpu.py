@@ -305,3 +305,69 @@ def test_tc_conv_transpose1d(cuda_device, Cin, Cout, k, u, T):
 def test_tc_conv_transpose1d_lengths(cuda_device):
     _tc_convt_case(cuda_device, 3, 64, 32, 8, 4, 300, lengths=[300, 1, 129])
     _tc_convt_case(cuda_device, 2, 512, 256, 11, 5, 128, lengths=[128, 77])
+
+
+# ---------------------------------------------------------------------------------------------
+# fused ResBlock pair (resblock_tc.cuh)
+# ---------------------------------------------------------------------------------------------
+def _pair_case(dev, B, C, T, k, d, acc=False, div=0.0, lengths=None, seed=0):
+    from dissc_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, T, generator=g)
+    w1 = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    w2 = 0.5 * torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b1, b2 = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    a = torch.randn(B, C, T, generator=g) if acc else None
+    outs = []
+    for b in range(B):   # reference semantics: every utterance alone, unpadded
+        n = T if lengths is None else lengths[b]
+        xb = x[b:b + 1, :, :n].double()
+        xt = F.conv1d(F.leaky_relu(xb, 0.1), w1.double(), b1.double(), padding=(k * d - d) // 2, dilation=d)
+        y = F.conv1d(F.leaky_relu(xt, 0.1), w2.double(), b2.double(), padding=(k - 1) // 2) + xb
+        if acc:
+            y = a[b:b + 1, :, :n].double() + y
+        if div:
+            y = y / div
+        full = torch.zeros(1, C, T, dtype=torch.float64)
+        full[:, :, :n] = y
+        outs.append(full)
+    want = torch.cat(outs).float()
+    xd = x.to(dev)
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            xd[i, :, n:] = float("nan")
+    raw = torch.full((B, C, T), float("nan"), device=dev)
+    pl = torch.full((B, C, T), float("nan"), device=dev)
+    ld = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=dev)
+    ad = None if a is None else a.to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dissc_resblock_pair_tc(_ptr(xd), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(ad), _ptr(raw),
+                                                     _ptr(pl), _ptr(ld), 1, B, C, T, k, d, float(div), 0.1, None))
+    torch.cuda.synchronize()
+    raw, pl = raw.cpu(), pl.cpu()
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            assert torch.all(pl[i, :, n:] == 0), "rows past the valid length must be stored as zeros"
+            raw[i, :, n:] = 0
+    assert torch.isfinite(raw).all() and torch.isfinite(pl).all()
+    assert (raw - want).abs().max().item() < 3e-5
+    assert (pl - F.leaky_relu(want, 0.1)).abs().max().item() < 3e-5
+
+
+@pytest.mark.parametrize("C", [16, 32])
+@pytest.mark.parametrize("k,d", [(3, 1), (3, 3), (3, 5), (7, 1), (7, 3), (7, 5), (11, 1), (11, 3), (11, 5)])
+def test_pair_resblock_shapes(cuda_device, C, k, d):
+    _pair_case(cuda_device, 2, C, 1000, k, d)
+
+
+@pytest.mark.parametrize("T", [1, 2, 117, 118, 119, 128, 1025])
+def test_pair_ragged_time(cuda_device, T):
+    _pair_case(cuda_device, 2, 32, T, 11, 5)
+    _pair_case(cuda_device, 3, 16, T, 3, 1, acc=True, div=3.0)
+
+
+def test_pair_many_tiles_and_lengths(cuda_device):
+    # far more tiles than SMs: both worker groups wrap all their pipeline phases many times
+    _pair_case(cuda_device, 6, 16, 126 * 160, 3, 1, acc=True)
+    _pair_case(cuda_device, 4, 32, 118 * 90 + 5, 11, 5, acc=True, div=3.0)
+    _pair_case(cuda_device, 4, 32, 700, 7, 3, lengths=[700, 1, 257, 433])
