@@ -131,20 +131,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
+// fp32 pair -> packed fp16x2, round to nearest, saturating to +-65504 (one F2FP.SATFINITE instruction)
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
 }
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 8 values -> one 16-byte store per plane
 __device__ __forceinline__ void split_store8(__half* hi_dst, __half* lo_dst, const float v[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float c0 = fminf(fmaxf(v[2 * i], -65504.f), 65504.f);
-    const float c1 = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
-    const __half2 hh = __floats2half2_rn(c0, c1);
-    const float2 back = __half22float2(hh);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = pack_half2(c0 - back.x, c1 - back.y);
+    h[i] = pack_half2_sat(v[2 * i], v[2 * i + 1]);
+    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+    l[i] = pack_half2_sat(v[2 * i] - back.x, v[2 * i + 1] - back.y);
   }
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);

@@ -51,7 +51,7 @@ struct PairParams {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(kPairThreads, 1) resblock_pair_tc_kernel(const PairParams p) {
+__global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pair_tc_kernel(const PairParams p) {
   constexpr int C8 = NC / 8;
   constexpr int KS = NC / 16;
   constexpr uint32_t lbo_b = 2u * NC * 16;
