@@ -252,15 +252,18 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
       {
         const int t = t0 - p2 + row;
         const bool v_ok = t >= 0 && t < Tvalid;
+        float m[C8][8], x8[C8][8];
+#pragma unroll
+        for (int c8 = 0; c8 < C8; ++c8) {   // all TMEM loads in flight, one wait
+          tmem_ld8(t_acc1 + c8 * 8, m[c8]);
+          tmem_ld8(t_acc1 + NC + c8 * 8, x8[c8]);
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int c8 = 0; c8 < C8; ++c8) {
-          float m[8], x8[8];
-          tmem_ld8(t_acc1 + c8 * 8, m);
-          tmem_ld8(t_acc1 + NC + c8 * 8, x8);
-          tmem_ld_wait();
           float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = v_ok ? leaky((m[e] + x8[e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f) : 0.f;
+          for (int e = 0; e < 8; ++e) v[e] = v_ok ? leaky((m[c8][e] + x8[c8][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f) : 0.f;
           const size_t o = ((size_t)c8 * R2 + row) * 16;
           split_store8(reinterpret_cast<__half*>(xt + o), reinterpret_cast<__half*>(xt + xt_plane + o), v);
         }
@@ -274,16 +277,23 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
       // ---- epilogue 2: acc2 + bias + residual [+ xs] [/ n] -> outputs
       mbar_wait(&acc2_full[g], ph);
       tc_fence_after();
+      float m2[C8][8], y2[C8][8];
 #pragma unroll
       for (int c8 = 0; c8 < C8; ++c8) {
-        float m[8], x8[8];
-        tmem_ld8(t_acc2 + c8 * 8, m);
-        tmem_ld8(t_acc2 + NC + c8 * 8, x8);
-        tmem_ld_wait();
+        tmem_ld8(t_acc2 + c8 * 8, m2[c8]);
+        tmem_ld8(t_acc2 + NC + c8 * 8, y2[c8]);
+      }
+      tmem_ld_wait();
+      // the accumulator is in registers: release it before the (long) store phase
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_empty[g]);
+#pragma unroll
+      for (int c8 = 0; c8 < C8; ++c8) {
         if (!out_valid && !(p.out_hi && row < M_out && t_out < p.T)) continue;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (m[e] + x8[e]) * p.inv2 + s_b2[c8 * 8 + e];
+        for (int e = 0; e < 8; ++e) v[e] = (m2[c8][e] + y2[c8][e]) * p.inv2 + s_b2[c8 * 8 + e];
         if (out_valid) {
           v[0] += rq[2 * c8].x; v[1] += rq[2 * c8].y; v[2] += rq[2 * c8].z; v[3] += rq[2 * c8].w;
           v[4] += rq[2 * c8 + 1].x; v[5] += rq[2 * c8 + 1].y; v[6] += rq[2 * c8 + 1].z; v[7] += rq[2 * c8 + 1].w;
@@ -315,9 +325,6 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
           split_store8(p.out_hi + o, p.out_lo + o, a);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc2_empty[g]);
     }
   }
 
