@@ -345,7 +345,7 @@ static int launch_pair_nc(const PairParams& p, const PairLayer& L, int grid, cud
                                     (int)(kSmemPerSm - 1024)));
     attr_set = true;
   }
-  resblock_pair_tc_kernel<NC><<<grid, kPairThreads, L.smem, st>>>(p);
+  resblock_pair_tc_kernel<NC><<<grid, PairCfg<NC>::THREADS, L.smem, st>>>(p);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }

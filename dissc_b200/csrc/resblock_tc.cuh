@@ -25,7 +25,16 @@
 
 namespace dissc {
 
-constexpr int kPairThreads = 320;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-5 / 6-9 worker groups
+// warp 0 producer, warp 1 MMA issuer + TMEM owner, then two worker groups of WPG warps each.  C=32: 8 warps per group
+// (two warps share a TMEM lane quarter and split the channel groups) -- one CTA per SM, so the extra warps are what
+// hides the epilogue latencies; C=16: 4 warps per group, two CTAs per SM.
+template <int NC>
+struct PairCfg {
+  static constexpr int WPG = (NC >= 32) ? 8 : 4;
+  static constexpr int THREADS = 64 + 2 * WPG * 32;
+  static constexpr int C8 = NC / 8;
+  static constexpr int CH = C8 * 4 / WPG;  // 8-channel groups per worker warp
+};
 
 struct PairParams {
   const float* x;       // f32h [B][C/8][Tpf][8]
@@ -51,8 +60,9 @@ struct PairParams {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pair_tc_kernel(const PairParams p) {
+__global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resblock_pair_tc_kernel(const PairParams p) {
   constexpr int C8 = NC / 8;
+  constexpr int WPG = PairCfg<NC>::WPG, CH = PairCfg<NC>::CH, kPairThreads = PairCfg<NC>::THREADS;
   constexpr int KS = NC / 16;
   constexpr uint32_t lbo_b = 2u * NC * 16;
   constexpr uint32_t w_tap_bytes = (uint32_t)C8 * lbo_b;
@@ -89,13 +99,13 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&stg_full[i], 1);
-      mbar_init(&stg_empty[i], 4);
-      mbar_init(&xop_full[i], 4);
+      mbar_init(&stg_empty[i], WPG);
+      mbar_init(&xop_full[i], WPG);
       mbar_init(&xop_empty[i], 1);
       mbar_init(&acc1_full[i], 1);
-      mbar_init(&xt_full[i], 4);
+      mbar_init(&xt_full[i], WPG);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], 4);
+      mbar_init(&acc2_empty[i], WPG);
     }
     mbar_init(&w_full[0], 1);
     fence_mbar_init();
@@ -182,9 +192,11 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
     }
   } else {
     // ===================== worker groups: convert -> epilogue 1 -> epilogue 2 =====================
-    const int g = (warp - 2) >> 2;          // 0: warps 2-5, 1: warps 6-9
+    const int g = (warp - 2) / WPG;         // worker group
+    const int wi = (warp - 2) - g * WPG;    // warp inside the group
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
-    const int wt = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the group
+    const int c8_0 = (wi >> 2) * CH;        // first of the CH channel groups this warp handles in the epilogues
+    const int wt = wi * 32 + lane;          // thread index inside the group
     const int row = quarter * 32 + lane;    // TMEM lane = tile row
     unsigned char* stg = sStg + g * stg_bytes;
     unsigned char* xop = sXop + g * xop_bytes;
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
       mbar_wait(&stg_full[g], ph);
       mbar_wait(&xop_empty[g], ph ^ 1);
       const int tx0 = t0 - p2 - p1;
-      for (int item = wt; item < C8 * R1; item += 128) {
+      for (int item = wt; item < C8 * R1; item += WPG * 32) {
         const int c8 = item / R1, i = item - c8 * R1;
         const int t = tx0 + i;
         float v[8];
@@ -233,16 +245,16 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
       // ---- residual (and MRF accumulator) prefetch for epilogue 2: row t0+row of the same fp32 tensor (L2-hot)
       const int t_out = t0 + row;
       const bool out_valid = row < M_out && t_out < Tvalid;
-      float4 rq[C8 * 2], aq[C8 * 2];
+      float4 rq[CH * 2], aq[CH * 2];
       if (out_valid) {
 #pragma unroll
-        for (int c8 = 0; c8 < C8; ++c8) {
-          const size_t fi = (((size_t)b * C8 + c8) * p.Tpf + p.f_halo + t_out) * 8;
-          rq[2 * c8] = *reinterpret_cast<const float4*>(p.x + fi);
-          rq[2 * c8 + 1] = *reinterpret_cast<const float4*>(p.x + fi + 4);
+        for (int q = 0; q < CH; ++q) {
+          const size_t fi = (((size_t)b * C8 + c8_0 + q) * p.Tpf + p.f_halo + t_out) * 8;
+          rq[2 * q] = *reinterpret_cast<const float4*>(p.x + fi);
+          rq[2 * q + 1] = *reinterpret_cast<const float4*>(p.x + fi + 4);
           if (p.acc_in) {
-            aq[2 * c8] = *reinterpret_cast<const float4*>(p.acc_in + fi);
-            aq[2 * c8 + 1] = *reinterpret_cast<const float4*>(p.acc_in + fi + 4);
+            aq[2 * q] = *reinterpret_cast<const float4*>(p.acc_in + fi);
+            aq[2 * q + 1] = *reinterpret_cast<const float4*>(p.acc_in + fi + 4);
           }
         }
       }
@@ -252,18 +264,19 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
       {
         const int t = t0 - p2 + row;
         const bool v_ok = t >= 0 && t < Tvalid;
-        float m[C8][8], x8[C8][8];
+        float m[CH][8], x8[CH][8];
 #pragma unroll
-        for (int c8 = 0; c8 < C8; ++c8) {   // all TMEM loads in flight, one wait
-          tmem_ld8(t_acc1 + c8 * 8, m[c8]);
-          tmem_ld8(t_acc1 + NC + c8 * 8, x8[c8]);
+        for (int q = 0; q < CH; ++q) {   // all TMEM loads in flight, one wait
+          tmem_ld8(t_acc1 + (c8_0 + q) * 8, m[q]);
+          tmem_ld8(t_acc1 + NC + (c8_0 + q) * 8, x8[q]);
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int c8 = 0; c8 < C8; ++c8) {
+        for (int q = 0; q < CH; ++q) {
+          const int c8 = c8_0 + q;
           float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = v_ok ? leaky((m[c8][e] + x8[c8][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f) : 0.f;
+          for (int e = 0; e < 8; ++e) v[e] = v_ok ? leaky((m[q][e] + x8[q][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f) : 0.f;
           const size_t o = ((size_t)c8 * R2 + row) * 16;
           split_store8(reinterpret_cast<__half*>(xt + o), reinterpret_cast<__half*>(xt + xt_plane + o), v);
         }
@@ -277,11 +290,11 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
       // ---- epilogue 2: acc2 + bias + residual [+ xs] [/ n] -> outputs
       mbar_wait(&acc2_full[g], ph);
       tc_fence_after();
-      float m2[C8][8], y2[C8][8];
+      float m2[CH][8], y2[CH][8];
 #pragma unroll
-      for (int c8 = 0; c8 < C8; ++c8) {
-        tmem_ld8(t_acc2 + c8 * 8, m2[c8]);
-        tmem_ld8(t_acc2 + NC + c8 * 8, y2[c8]);
+      for (int q = 0; q < CH; ++q) {
+        tmem_ld8(t_acc2 + (c8_0 + q) * 8, m2[q]);
+        tmem_ld8(t_acc2 + NC + (c8_0 + q) * 8, y2[q]);
       }
       tmem_ld_wait();
       // the accumulator is in registers: release it before the (long) store phase
@@ -289,18 +302,19 @@ __global__ void __launch_bounds__(kPairThreads, (NC == 16) ? 2 : 1) resblock_pai
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc2_empty[g]);
 #pragma unroll
-      for (int c8 = 0; c8 < C8; ++c8) {
+      for (int q = 0; q < CH; ++q) {
+        const int c8 = c8_0 + q;
         if (!out_valid && !(p.out_hi && row < M_out && t_out < p.T)) continue;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (m2[c8][e] + y2[c8][e]) * p.inv2 + s_b2[c8 * 8 + e];
+        for (int e = 0; e < 8; ++e) v[e] = (m2[q][e] + y2[q][e]) * p.inv2 + s_b2[c8 * 8 + e];
         if (out_valid) {
-          v[0] += rq[2 * c8].x; v[1] += rq[2 * c8].y; v[2] += rq[2 * c8].z; v[3] += rq[2 * c8].w;
-          v[4] += rq[2 * c8 + 1].x; v[5] += rq[2 * c8 + 1].y; v[6] += rq[2 * c8 + 1].z; v[7] += rq[2 * c8 + 1].w;
+          v[0] += rq[2 * q].x; v[1] += rq[2 * q].y; v[2] += rq[2 * q].z; v[3] += rq[2 * q].w;
+          v[4] += rq[2 * q + 1].x; v[5] += rq[2 * q + 1].y; v[6] += rq[2 * q + 1].z; v[7] += rq[2 * q + 1].w;
           if (p.acc_in) {
-            v[0] = aq[2 * c8].x + v[0]; v[1] = aq[2 * c8].y + v[1]; v[2] = aq[2 * c8].z + v[2]; v[3] = aq[2 * c8].w + v[3];
-            v[4] = aq[2 * c8 + 1].x + v[4]; v[5] = aq[2 * c8 + 1].y + v[5]; v[6] = aq[2 * c8 + 1].z + v[6];
-            v[7] = aq[2 * c8 + 1].w + v[7];
+            v[0] = aq[2 * q].x + v[0]; v[1] = aq[2 * q].y + v[1]; v[2] = aq[2 * q].z + v[2]; v[3] = aq[2 * q].w + v[3];
+            v[4] = aq[2 * q + 1].x + v[4]; v[5] = aq[2 * q + 1].y + v[5]; v[6] = aq[2 * q + 1].z + v[6];
+            v[7] = aq[2 * q + 1].w + v[7];
           }
           if (p.div != 0.f) {
 #pragma unroll
