@@ -36,7 +36,13 @@
 
 namespace dissc {
 
-constexpr int kTcThreads = 192;
+// CTA size: producer warp + MMA warp + epilogue warps.  N >= 128 uses 8 epilogue warps (two per TMEM lane quarter, each
+// taking half of the columns): one CTA per SM there, and a 128 x N tile is too much epilogue for 4 warps to hide.
+template <int NC>
+struct TcCfg {
+  static constexpr int EPW = (NC >= 128) ? 8 : 4;
+  static constexpr int THREADS = 64 + EPW * 32;
+};
 constexpr int kTcHalo = 32;       // zero rows either side of every plane row-slab (>= max conv padding 25)
 constexpr int kTcMaxStages = 64;  // barrier slots for the weight pipeline (resident mode: one per stage)
 
@@ -151,7 +157,8 @@ __device__ __forceinline__ void split_store8(__half* hi_dst, __half* lo_dst, con
 }
 
 template <int NC>
-__global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 : 1)) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 64) ? 2 : 1)) conv_tc_kernel(const TcParams p) {
+  constexpr int EPW = TcCfg<NC>::EPW, kTcThreads = TcCfg<NC>::THREADS;
   constexpr bool kTwoMma = (NC <= 128);
   constexpr int G = NC / 8;            // 8-channel groups per chunk
   constexpr int EB = 2;                // groups per epilogue batch
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], EPW);
     }
     for (int i = 0; i < p.NS; ++i) {
       mbar_init(&w_full[i], 1);
@@ -317,6 +324,8 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
   } else {
     // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
     const int quarter = warp & 3;
+    constexpr int NBH = NB / (EPW / 4);                 // epilogue batches per warp
+    const int bi0 = ((warp - 2) >> 2) * NBH;            // this warp's first batch (column half)
     const int row = quarter * 32 + lane;
     const int cout8 = p.Cout / 8;
     uint32_t ab = 0, accph = 0;
@@ -335,22 +344,22 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
       if (p.res && conv_valid) {
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
-          rq[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + e * fstride);
-          rq[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + e * fstride + 4);
+          rq[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + (bi0 * EB + e) * fstride);
+          rq[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + (bi0 * EB + e) * fstride + 4);
         }
       }
       if (kAccPrefetch && p.acc_in && conv_valid) {
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
-          aq[2 * e] = *reinterpret_cast<const float4*>(p.acc_in + fbase + e * fstride);
-          aq[2 * e + 1] = *reinterpret_cast<const float4*>(p.acc_in + fbase + e * fstride + 4);
+          aq[2 * e] = *reinterpret_cast<const float4*>(p.acc_in + fbase + (bi0 * EB + e) * fstride);
+          aq[2 * e + 1] = *reinterpret_cast<const float4*>(p.acc_in + fbase + (bi0 * EB + e) * fstride + 4);
         }
       }
       mbar_wait(&acc_full[ab], accph);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * (uint32_t)p.acc_cols;
 #pragma unroll 1
-      for (int bi = 0; bi < NB; ++bi) {
+      for (int bi = bi0; bi < bi0 + NBH; ++bi) {
         float m[EB][8], x[EB][8];
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
           if (!p.single_acc) tmem_ld8(taddr0 + NC + (bi * EB + e) * 8, x[e]);
         }
         float4 rn[EB * 2];
-        if (NB > 1 && bi + 1 < NB && p.res && conv_valid) {
+        if (NBH > 1 && bi + 1 < bi0 + NBH && p.res && conv_valid) {
           // prefetch the next batch's residual while this one is processed
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
           }
         }
         float4 an[EB * 2];
-        if (kAccPrefetch && NB > 1 && bi + 1 < NB && p.acc_in && conv_valid) {
+        if (kAccPrefetch && NBH > 1 && bi + 1 < bi0 + NBH && p.acc_in && conv_valid) {
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
             an[2 * e] = *reinterpret_cast<const float4*>(p.acc_in + fbase + ((bi + 1) * EB + e) * fstride);
@@ -447,7 +456,7 @@ __global__ void __launch_bounds__(kTcThreads, (NC <= 32) ? 3 : ((NC <= 64) ? 2 :
             split_store8(p.out_hi + pidx, p.out_lo + pidx, a);
           }
         }
-        if (NB > 1) {
+        if (NBH > 1) {
 #pragma unroll
           for (int e = 0; e < EB * 2; ++e) {
             rq[e] = rn[e];

@@ -267,7 +267,7 @@ static int launch_conv_tc_nc(const TcParams& p, const TcLayer& L, int grid, cuda
                                     (int)(kSmemPerSm - 1024)));
     attr_set = true;
   }
-  conv_tc_kernel<NC><<<grid, kTcThreads, L.smem, st>>>(p);
+  conv_tc_kernel<NC><<<grid, TcCfg<NC>::THREADS, L.smem, st>>>(p);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
