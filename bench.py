@@ -95,8 +95,8 @@ def cpu_port_time(B, T, steps, warmup, threads=None):
     """Times the oracle port (reference algorithm, ATen/oneDNN on the host) -> (samples/s, ms/step, cores)."""
     from dissc_b200 import synthetic as syn
     from oracle import generator_oracle as go
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on explicitly
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
     sd = go.folded_state_dict(syn.synthetic_generator_state_dict(syn.VCTK_CONFIG, seed=0))
     code, f0, spkr = syn.synthetic_inputs(B, T, seed=1234)
