@@ -36,13 +36,9 @@
 
 namespace dissc {
 
-// CTA size: producer warp + MMA warp + epilogue warps.  N >= 128 uses 8 epilogue warps (two per TMEM lane quarter, each
-// taking half of the columns): one CTA per SM there, and a 128 x N tile is too much epilogue for 4 warps to hide.
-template <int NC>
-struct TcCfg {
-  static constexpr int EPW = (NC >= 128) ? 8 : 4;
-  static constexpr int THREADS = 64 + EPW * 32;
-};
+// CTA = producer warp + MMA warp + EPW epilogue warps.  N >= 128 (and N = 64 when one CTA fills the SM) uses 8 epilogue
+// warps, two per TMEM lane quarter, each taking half of the columns: a 128 x N tile is too much epilogue for 4 warps to
+// hide behind the MMAs of the next tile.
 constexpr int kTcHalo = 32;       // zero rows either side of every plane row-slab (>= max conv padding 25)
 constexpr int kTcMaxStages = 64;  // barrier slots for the weight pipeline (resident mode: one per stage)
 
@@ -88,6 +84,7 @@ struct TcParams {
                          //   > 0 = the "f32h" layout of resblock_tc.cuh, with Tr = rows per slab incl. slack)
   int groups;            // grouped conv: chunk g reads channel blocks [g*n_cb, (g+1)*n_cb) and writes group_c8 8-channel
   int group_c8;          //   groups of output channels starting at g*group_c8 (NC >= 8*group_c8, padded columns dropped)
+  int cout_log2;         // log2(Cout) when Cout is a power of two, else -1 (kTcUp needs it)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -156,10 +153,60 @@ __device__ __forceinline__ void split_store8(__half* hi_dst, __half* lo_dst, con
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int NC>
-__global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 64) ? 2 : 1)) conv_tc_kernel(const TcParams p) {
-  constexpr int EPW = TcCfg<NC>::EPW, kTcThreads = TcCfg<NC>::THREADS;
+// MODE selects how much of the epilogue is compiled in (the runtime switches of TcParams cost instructions in the
+// per-element loops, and the narrow layers are bound by exactly that):
+//   kTcGeneric : everything (HuBERT: GELU, grouped / de-interleaved outputs, plain outputs, ...)
+//   kTcConv    : vocoder Conv1d -- bias [+ residual] [+ MRF accumulate] [/ n] -> f32b and/or leaky-relu planes
+//   kTcUp      : vocoder polyphase ConvTranspose1d -- bias -> f32b and/or leaky-relu planes (Cout a power of two)
+enum { kTcGeneric = 0, kTcConv = 1, kTcUp = 2 };
+
+// 32-byte global accesses (one f32b row of 8 channels): LDG.E.256 / STG.E.256 on sm_100
+__device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg8(float* p, const float v[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+// one f32b row (8 floats): a single 32-byte access where the caller guarantees 32-byte alignment (WIDE), else two float4
+template <bool WIDE>
+__device__ __forceinline__ void ld_row8(const float* p, float4& a, float4& b) {
+  if constexpr (WIDE) {
+    ldg8(p, a, b);
+  } else {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+}
+template <bool WIDE>
+__device__ __forceinline__ void st_row8(float* p, const float v[8]) {
+  if constexpr (WIDE) {
+    stg8(p, v);
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+template <int NC, int EPW, int MODE>
+__global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 3 : 2)) conv_tc_kernel(const TcParams p) {
+  constexpr int kTcThreads = 64 + EPW * 32;
   constexpr bool kTwoMma = (NC <= 128);
+  constexpr bool kFast = (MODE != kTcGeneric);
+  // switches the specialised modes fold away at compile time
+  const int up = (MODE == kTcConv) ? 0 : p.up;
+  const int groups = kFast ? 0 : p.groups;
+  const int pre_act = kFast ? 0 : p.pre_act;
+  const int out_deint = kFast ? 0 : p.out_deint;
+  float* const out_plain = kFast ? nullptr : p.out_plain;
+  const float* const res_p = (MODE == kTcUp) ? nullptr : p.res;
+  const float* const acc_p = (MODE == kTcUp) ? nullptr : p.acc_in;
+  const float div = p.div;  // unused by kTcUp
+  const int single_acc = (NC == 256) ? p.single_acc : 0;
   constexpr int G = NC / 8;            // 8-channel groups per chunk
   constexpr int EB = 2;                // groups per epilogue batch
   constexpr int NB = G / EB;
@@ -202,8 +249,8 @@ __global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 6
     fence_mbar_init();
   }
   for (int i = tid; i < p.n_chunks * NC; i += kTcThreads) {
-    int co = p.up ? (i % p.Cout) : i;
-    if (p.groups) {
+    int co = up ? (i % p.Cout) : i;
+    if (groups) {
       const int ch = i / NC, n = i - ch * NC;
       co = n < p.group_c8 * 8 ? ch * p.group_c8 * 8 + n : p.Cout;
     }
@@ -230,7 +277,7 @@ __global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 6
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int b = tile / p.tiles_per_b;
         const int r0 = (tile - b * p.tiles_per_b) * 128;
-        const size_t in0 = (((size_t)b * p.Cin8 + (p.groups ? (size_t)chunk * p.n_cb * kb8 : 0)) * p.Tp_in + p.halo + r0 -
+        const size_t in0 = (((size_t)b * p.Cin8 + (groups ? (size_t)chunk * p.n_cb * kb8 : 0)) * p.Tp_in + p.halo + r0 -
                             p.pad) * 8;
         const __half* hi0 = p.a_hi + in0;
         const __half* lo0 = p.a_lo + in0;
@@ -280,7 +327,7 @@ __global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 6
         mbar_wait(&acc_empty[ab], accph ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base + ab * (uint32_t)p.acc_cols;
-        const uint32_t d_cross = p.single_acc ? d_main : d_main + NC;
+        const uint32_t d_cross = single_acc ? d_main : d_main + NC;
         uint32_t accum = 0;
         for (int cb = 0; cb < p.n_cb; ++cb) {
           mbar_wait(&a_full[abuf], aph);
@@ -304,7 +351,7 @@ __global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 6
                   umma_f16(d_cross, umma_desc(ad + a_lo_off), umma_desc(wd), idesc_n, 1);     // cross += lo*hi
                 } else {
                   umma_f16(d_main, umma_desc(ad), umma_desc(wd), idesc_n, accum);
-                  umma_f16(d_cross, umma_desc(ad + a_lo_off), umma_desc(wd), idesc_n, p.single_acc ? 1u : accum);
+                  umma_f16(d_cross, umma_desc(ad + a_lo_off), umma_desc(wd), idesc_n, single_acc ? 1u : accum);
                   umma_f16(d_cross, umma_desc(ad), umma_desc(wd + NC), idesc_n, 1);
                 }
                 accum = 1;
@@ -337,22 +384,20 @@ __global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 6
       const int Tvalid = p.lengths ? min(p.T, p.lengths[b] * p.len_mul) : p.T;
       // residual of the first batch: issued before the accumulator wait so its latency hides behind the MMAs
       float4 rq[EB * 2];
-      const bool conv_valid = (!p.up) && r < Tvalid;
-      const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * (p.groups ? p.group_c8 : G)) * p.Tr + p.f_halo + r) * 8;
+      const bool conv_valid = (!up) && r < Tvalid;
+      const size_t fbase = (((size_t)b * cout8 + (size_t)chunk * (groups ? p.group_c8 : G)) * p.Tr + p.f_halo + r) * 8;
       const size_t fstride = (size_t)p.Tr * 8;
       float4 aq[EB * 2];
-      if (p.res && conv_valid) {
+      if (res_p && conv_valid) {
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
-          rq[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + (bi0 * EB + e) * fstride);
-          rq[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + (bi0 * EB + e) * fstride + 4);
+          ld_row8<kFast>(res_p + fbase + (bi0 * EB + e) * fstride, rq[2 * e], rq[2 * e + 1]);
         }
       }
-      if (kAccPrefetch && p.acc_in && conv_valid) {
+      if (kAccPrefetch && acc_p && conv_valid) {
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
-          aq[2 * e] = *reinterpret_cast<const float4*>(p.acc_in + fbase + (bi0 * EB + e) * fstride);
-          aq[2 * e + 1] = *reinterpret_cast<const float4*>(p.acc_in + fbase + (bi0 * EB + e) * fstride + 4);
+          ld_row8<kFast>(acc_p + fbase + (bi0 * EB + e) * fstride, aq[2 * e], aq[2 * e + 1]);
         }
       }
       mbar_wait(&acc_full[ab], accph);
@@ -364,23 +409,21 @@ __global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 6
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
           tmem_ld8(taddr0 + (bi * EB + e) * 8, m[e]);
-          if (!p.single_acc) tmem_ld8(taddr0 + NC + (bi * EB + e) * 8, x[e]);
+          if (!single_acc) tmem_ld8(taddr0 + NC + (bi * EB + e) * 8, x[e]);
         }
         float4 rn[EB * 2];
-        if (NBH > 1 && bi + 1 < bi0 + NBH && p.res && conv_valid) {
+        if (NBH > 1 && bi + 1 < bi0 + NBH && res_p && conv_valid) {
           // prefetch the next batch's residual while this one is processed
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
-            rn[2 * e] = *reinterpret_cast<const float4*>(p.res + fbase + ((bi + 1) * EB + e) * fstride);
-            rn[2 * e + 1] = *reinterpret_cast<const float4*>(p.res + fbase + ((bi + 1) * EB + e) * fstride + 4);
+            ld_row8<kFast>(res_p + fbase + ((bi + 1) * EB + e) * fstride, rn[2 * e], rn[2 * e + 1]);
           }
         }
         float4 an[EB * 2];
-        if (kAccPrefetch && NBH > 1 && bi + 1 < bi0 + NBH && p.acc_in && conv_valid) {
+        if (kAccPrefetch && NBH > 1 && bi + 1 < bi0 + NBH && acc_p && conv_valid) {
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
-            an[2 * e] = *reinterpret_cast<const float4*>(p.acc_in + fbase + ((bi + 1) * EB + e) * fstride);
-            an[2 * e + 1] = *reinterpret_cast<const float4*>(p.acc_in + fbase + ((bi + 1) * EB + e) * fstride + 4);
+            ld_row8<kFast>(acc_p + fbase + ((bi + 1) * EB + e) * fstride, an[2 * e], an[2 * e + 1]);
           }
         }
         tmem_ld_wait();
@@ -391,69 +434,74 @@ __global__ void __launch_bounds__(TcCfg<NC>::THREADS, (NC <= 32) ? 3 : ((NC <= 6
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float s = p.single_acc ? m[e][i] : (m[e][i] + x[e][i]);
+            const float s = single_acc ? m[e][i] : (m[e][i] + x[e][i]);
             v[i] = s * p.w_inv_scale + s_bias[n0 + i];
           }
           int t, c8o;
           bool inb, valid;
-          if (p.up) {
-            const int phase = n0 / p.Cout;
+          if (up) {
+            const int phase = (MODE == kTcUp) ? (n0 >> p.cout_log2) : (n0 / p.Cout);
             c8o = (n0 - phase * p.Cout) >> 3;
-            t = r * p.up + phase - p.up_pad;
+            t = r * up + phase - p.up_pad;
             inb = t >= 0 && t < p.T;
             valid = inb && t < Tvalid;
           } else {
-            c8o = p.groups ? chunk * p.group_c8 + g8 : (n0 >> 3);
+            c8o = groups ? chunk * p.group_c8 + g8 : (n0 >> 3);
             t = r;
             inb = true;
             valid = conv_valid;
-            if (p.groups && g8 >= p.group_c8) continue;  // padded output columns of a group
+            if (groups && g8 >= p.group_c8) continue;  // padded output columns of a group
           }
-          if (c8o >= cout8) continue;  // padded output columns
-          if (p.pre_act) {
+          if (!kFast && c8o >= cout8) continue;  // padded output columns
+          if (pre_act) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = tc_act(v[i], p.pre_act, 0.f);
+            for (int i = 0; i < 8; ++i) v[i] = tc_act(v[i], pre_act, 0.f);
           }
           const size_t fidx = (((size_t)b * cout8 + c8o) * p.Tr + p.f_halo + t) * 8;
           if (valid) {
-            if (p.res) {
+            if (res_p) {
               v[0] += rq[2 * e].x; v[1] += rq[2 * e].y; v[2] += rq[2 * e].z; v[3] += rq[2 * e].w;
               v[4] += rq[2 * e + 1].x; v[5] += rq[2 * e + 1].y; v[6] += rq[2 * e + 1].z; v[7] += rq[2 * e + 1].w;
             }
-            if (p.acc_in) {
+            if (acc_p) {
               float4 r0, r1;
               if constexpr (kAccPrefetch) {
                 r0 = aq[2 * e]; r1 = aq[2 * e + 1];
               } else {
-                r0 = *reinterpret_cast<const float4*>(p.acc_in + fidx);
-                r1 = *reinterpret_cast<const float4*>(p.acc_in + fidx + 4);
+                ld_row8<kFast>(acc_p + fidx, r0, r1);
               }
               v[0] = r0.x + v[0]; v[1] = r0.y + v[1]; v[2] = r0.z + v[2]; v[3] = r0.w + v[3];
               v[4] = r1.x + v[4]; v[5] = r1.y + v[5]; v[6] = r1.z + v[6]; v[7] = r1.w + v[7];
             }
-            if (p.div != 0.f) {
+            if constexpr (MODE != kTcUp) {
+              if (div != 0.f) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = v[i] / p.div;
+                for (int i = 0; i < 8; ++i) v[i] = v[i] / div;
+              }
             }
             if (p.out_f32b) {
-              *reinterpret_cast<float4*>(p.out_f32b + fidx) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(p.out_f32b + fidx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              st_row8<kFast>(p.out_f32b + fidx, v);
             }
-            if (p.out_plain) {
+            if (out_plain) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                p.out_plain[((size_t)b * p.Cout + c8o * 8 + i) * p.T + t] = tc_act(v[i], p.plain_act, p.plain_slope);
+                out_plain[((size_t)b * p.Cout + c8o * 8 + i) * p.T + t] = tc_act(v[i], p.plain_act, p.plain_slope);
             }
           }
           if (p.out_hi && inb) {
             // rows >= valid length are written as zeros: they are the next conv's zero padding
-            float a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = valid ? tc_act(v[i], p.plane_act, p.plane_slope) : 0.f;
-            const size_t pidx = p.out_deint
+            const size_t pidx = out_deint
                                     ? (((size_t)b * 2 * cout8 + (size_t)(t & 1) * cout8 + c8o) * p.Tp + p.halo + (t >> 1)) * 8
                                     : (((size_t)b * cout8 + c8o) * p.Tp + p.halo + t) * 8;
-            split_store8(p.out_hi + pidx, p.out_lo + pidx, a);
+            if (valid) {
+              float a[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] = kFast ? leaky(v[i], p.plane_slope) : tc_act(v[i], p.plane_act, p.plane_slope);
+              split_store8(p.out_hi + pidx, p.out_lo + pidx, a);
+            } else {
+              *reinterpret_cast<uint4*>(p.out_hi + pidx) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(p.out_lo + pidx) = make_uint4(0, 0, 0, 0);
+            }
           }
         }
         if (NBH > 1) {

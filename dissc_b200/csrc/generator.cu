@@ -25,6 +25,7 @@
 #include "launch.cuh"
 #include "tc_host.cuh"
 #include "resblock_tc.cuh"
+#include "resblock64_tc.cuh"
 
 namespace dissc {
 
@@ -259,17 +260,49 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int NC>
-static int launch_conv_tc_nc(const TcParams& p, const TcLayer& L, int grid, cudaStream_t st) {
+template <int NC, int EPW, int MODE>
+static int launch_conv_tc_inst(const TcParams& p, const TcLayer& L, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DISSC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DISSC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NC, EPW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(kSmemPerSm - 1024)));
     attr_set = true;
   }
-  conv_tc_kernel<NC><<<grid, TcCfg<NC>::THREADS, L.smem, st>>>(p);
+  conv_tc_kernel<NC, EPW, MODE><<<grid, 64 + EPW * 32, L.smem, st>>>(p);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
+}
+
+template <int NC, int EPW>
+static int launch_conv_tc_mode(const TcParams& p, const TcLayer& L, int mode, int grid, cudaStream_t st) {
+  switch (mode) {
+    case kTcConv: return launch_conv_tc_inst<NC, EPW, kTcConv>(p, L, grid, st);
+    case kTcUp: return launch_conv_tc_inst<NC, EPW, kTcUp>(p, L, grid, st);
+  }
+  if constexpr (NC == 64 && EPW == 8) {
+    return set_err(DISSC_EINVAL, "no generic 8-warp N=64 kernel");
+  } else {
+    return launch_conv_tc_inst<NC, EPW, kTcGeneric>(p, L, grid, st);
+  }
+}
+
+// DISSC_TC_FAST=0: always the generic epilogue.  DISSC_TC_EPW64=4: four (not eight) epilogue warps for the one-CTA-per-SM
+// N=64 layers.  Both exist for A/B measurements (scripts/profile_layers.py).
+static int g_tc_fast = -1, g_tc_epw64 = -1;
+
+static bool aligned32(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; }
+
+// Which specialised epilogue (conv_tc.cuh MODE) serves this launch; kTcGeneric when any rarely used switch is on.
+static int tc_mode(const TcParams& p, const TcLayer& L) {
+  if (g_tc_fast < 0) {
+    const char* e = getenv("DISSC_TC_FAST");
+    g_tc_fast = e ? (atoi(e) != 0) : 1;
+  }
+  if (!g_tc_fast || p.groups || p.pre_act || p.out_deint || p.out_plain || (p.out_hi && p.plane_act != 1)) return kTcGeneric;
+  if (!aligned32(p.res) || !aligned32(p.acc_in) || !aligned32(p.out_f32b)) return kTcGeneric;
+  if (!L.up) return (L.n_chunks * L.NC == L.Cout) ? kTcConv : kTcGeneric;
+  if (p.res || p.acc_in || p.div != 0.f || p.cout_log2 < 0) return kTcGeneric;
+  return kTcUp;
 }
 
 // p carries the tensors, B, T (output rows), Tr, Tp, Tp_in, lengths and the epilogue switches; `rows` is the number of
@@ -282,15 +315,27 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale;
   p.Cin8 = L.cin8_total ? L.cin8_total : L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
   p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
+  p.cout_log2 = -1;
+  for (int s = 3; s < 12; ++s)
+    if ((1 << s) == L.Cout) p.cout_log2 = s;
   p.tiles_per_b = (rows + 127) / 128;
   p.n_items = p.B * p.tiles_per_b * L.n_chunks;
   const int grid = std::min(p.n_items, num_sms() * L.ctas_per_sm);
+  const int mode = tc_mode(p, L);
+  if (g_tc_epw64 < 0) {
+    const char* e = getenv("DISSC_TC_EPW64");
+    g_tc_epw64 = e ? atoi(e) : 8;
+  }
   switch (L.NC) {
-    case 16: return launch_conv_tc_nc<16>(p, L, grid, st);
-    case 32: return launch_conv_tc_nc<32>(p, L, grid, st);
-    case 64: return launch_conv_tc_nc<64>(p, L, grid, st);
-    case 128: return launch_conv_tc_nc<128>(p, L, grid, st);
-    case 256: return launch_conv_tc_nc<256>(p, L, grid, st);
+    case 16: return launch_conv_tc_mode<16, 4>(p, L, mode, grid, st);
+    case 32: return launch_conv_tc_mode<32, 4>(p, L, mode, grid, st);
+    case 64:
+      // a lone CTA per SM (weights of the k = 7 / 11 layers fill shared memory): four epilogue warps cannot keep up
+      // with the tensor pipe, eight can
+      if (L.ctas_per_sm == 1 && g_tc_epw64 == 8 && mode != kTcGeneric) return launch_conv_tc_mode<64, 8>(p, L, mode, grid, st);
+      return launch_conv_tc_mode<64, 4>(p, L, mode, grid, st);
+    case 128: return launch_conv_tc_mode<128, 8>(p, L, mode, grid, st);
+    case 256: return launch_conv_tc_mode<256, 8>(p, L, mode, grid, st);
   }
   return set_err(DISSC_EINVAL, "bad tensor-core chunk width %d", L.NC);
 }
@@ -362,6 +407,62 @@ static int launch_pair(PairParams p, const PairLayer& L, const TcLayer& c1, cons
 }
 
 // ------------------------------------------------------------------------
+// fused ResBlock pair, C = 64 (resblock64_tc.cuh): planes in / planes out, streamed weights
+// ------------------------------------------------------------------------
+static int g_use_pair64 = -1;  // DISSC_TC_PAIR64=0 disables it (the stage then runs the unfused c1 / c2 launches)
+
+struct Pair64Layer {
+  bool ok = false;
+  int k = 0, dil = 1, NS = 0;
+  size_t smem = 0;
+};
+
+static bool pair64_plan(int C, int k, int dil, const TcLayer& c1, const TcLayer& c2, Pair64Layer* L) {
+  L->ok = false;
+  if (g_use_pair64 < 0) {
+    const char* e = getenv("DISSC_TC_PAIR64");
+    g_use_pair64 = e ? (atoi(e) != 0) : 1;
+  }
+  if (!g_use_pair64 || C != 64 || !(k & 1) || k < 1 || k > 33) return false;
+  // weights as packed for conv_tc with KB = 32: [cb = 2][tap][c8 = 4][hi|lo][64][8]
+  if (!c1.ok || !c2.ok || c1.NC != 64 || c2.NC != 64 || c1.n_chunks != 1 || c2.n_chunks != 1 || c1.KB != 32 || c2.KB != 32 ||
+      c1.n_cb != 2 || c2.n_cb != 2)
+    return false;
+  const int p1 = dil * (k - 1) / 2, p2 = (k - 1) / 2;
+  if (p1 + p2 > kTcHalo || 128 - (k - 1) < 64) return false;
+  const size_t R1 = 128 + (size_t)(k - 1) * dil, R2 = 128 + (k - 1);
+  const size_t tiles = 2 * (2 * 8 * R1 * 16 + 2 * 8 * R2 * 16);
+  const size_t fixed = tiles + 2 * 64 * 4 + 128;
+  for (int ns = std::min(8, 2 * k); ns >= 2; --ns) {
+    const size_t need = fixed + (size_t)ns * kPair64TapBytes + (size_t)(12 + 2 * ns) * 8;
+    if (need <= kSmemPerSm - 1536) {
+      L->k = k; L->dil = dil; L->NS = ns; L->smem = need; L->ok = true;
+      return true;
+    }
+  }
+  return false;
+}
+
+static int launch_pair64(Pair64Params p, const Pair64Layer& L, const TcLayer& c1, const TcLayer& c2, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DISSC_CUDA(cudaFuncSetAttribute(resblock_pair64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSmemPerSm - 1024)));
+    attr_set = true;
+  }
+  p.k = L.k; p.dil = L.dil; p.NS = L.NS;
+  p.w1 = c1.w; p.w2 = c2.w; p.inv1 = c1.inv_scale; p.inv2 = c2.inv_scale;
+  if (p.halo == 0) p.halo = kTcHalo;
+  const int m_out = 128 - (L.k - 1);
+  p.tiles_per_b = (p.T + m_out - 1) / m_out;
+  p.n_tiles = p.B * p.tiles_per_b;
+  const int grid = std::min(p.n_tiles, num_sms());
+  resblock_pair64_tc_kernel<<<grid, kPair64Threads, L.smem, st>>>(p);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
+// ------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------
 struct ConvLayer {
@@ -404,6 +505,8 @@ struct dissc_gen {
   bool stage_tc[DISSC_MAX_STAGES] = {};
   PairLayer rb_pair[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // fused (c1,c2) pairs, narrow stages
   bool stage_pair[DISSC_MAX_STAGES] = {};
+  dissc::Pair64Layer rb_pair64[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // fused pairs of the C = 64 stage
+  bool stage_pair64[DISSC_MAX_STAGES] = {};
   TcLayer pre_tc, ups_tc[DISSC_MAX_STAGES];  // conv_pre / upsamplers on the tensor cores
   bool tc_all = false;                        // every layer but conv_post has a tcgen05 plan: planes flow end to end
   int use_tc = 1;
@@ -665,6 +768,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     const int ch = U.Cout;
     const bool last_stage = (i == c.n_up - 1);
     const bool pair = tc_all && g->stage_pair[i];            // fused (c1,c2) pairs on fp32 "f32h" tensors
+    const bool pair64 = tc_all && g->stage_pair64[i];        // fused (c1,c2) pairs on planes (C = 64)
     const int Tpf = Tr + kPairSlack;
     if (tc) {
       // zero padding of the plane pairs this stage writes (halo rows + round-up rows)
@@ -696,6 +800,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
       if (pair) {  // the fused pairs read x as fp32 only
         p.out_hi = nullptr; p.out_lo = nullptr; p.Tr = Tpf; p.f_halo = kPairHalo;
       }
+      if (pair64) p.out_f32b = nullptr;  // the C = 64 fused pairs read (and rebuild the residual from) the planes only
       const int n_frames = (Tout + U.pad - 1) / U.u + 1;
       DISSC_TRY(launch_conv_tc(p, g->ups_tc[i], n_frames, st));
     } else {
@@ -749,6 +854,33 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
           snprintf(name, sizeof(name), "s%d.rb%d.pair.%d.ptc", i, j, m);
           DISSC_TRY(L.begin(name, 2 * fl, by1 + by2));
           DISSC_TRY(launch_pair(q, g->rb_pair[i][j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], st));
+          DISSC_TRY(L.end());
+          continue;
+        }
+        if (pair64) {
+          // K3+K4 fused, planes in / planes out; the residual is rebuilt from the input planes (resblock64_tc.cuh)
+          const Planes PP[2] = {P_r, P_xt};  // ping-pong (a tile reads halo rows its neighbours write)
+          const Planes pin = (m == 0) ? P_up : PP[(m - 1) & 1];
+          Pair64Params q{};
+          q.x_hi = pin.hi; q.x_lo = pin.lo; q.in_inv_slope = 10.0f;  // planes hold lrelu(x, 0.1)
+          q.b1 = c1.bias; q.b2 = g->rb[i][j][m][1].bias;
+          q.lengths = lengths; q.len_mul = mul;
+          q.B = B; q.T = Tcur; q.Tp = Tp; q.Tr = Tr; q.halo = kTcHalo;
+          q.plane_slope = 0.1f;
+          if (!last_m) {
+            q.out_hi = PP[m & 1].hi; q.out_lo = PP[m & 1].lo;
+          } else {
+            if (j > 0) q.acc_in = F_xs;
+            if (!last_j) {
+              q.out_f = F_xs;
+            } else {
+              q.div = (float)c.n_rk;
+              q.out_hi = P_act[cur ^ 1].hi; q.out_lo = P_act[cur ^ 1].lo; q.plane_slope = next_slope;
+            }
+          }
+          snprintf(name, sizeof(name), "s%d.rb%d.pair.%d.p64", i, j, m);
+          DISSC_TRY(L.begin(name, 2 * fl, by1 + by2));
+          DISSC_TRY(launch_pair64(q, g->rb_pair64[i][j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], st));
           DISSC_TRY(L.end());
           continue;
         }
@@ -852,6 +984,79 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
   return DISSC_OK;
 }
 
+// Layer-level test of the C = 64 fused pair: plain (B,64,T) fp32 in, raw x' [+acc][/div] and leaky-relu planes out.
+static int pair64_layer_test(const float* in, const float* w1_host, const float* b1_host, const float* w2_host,
+                             const float* b2_host, const float* acc_in, float* out_raw, float* out_planes,
+                             const int32_t* lengths, int len_mul, int B, int T, int k, int dilation, float div,
+                             float plane_slope, cudaStream_t st) {
+  const int C = 64;
+  TcLayer c1, c2;
+  Pair64Layer L;
+  DISSC_CHECK(tc_plan_conv(C, C, k, dilation, &c1) && tc_plan_conv(C, C, k, 1, &c2) && pair64_plan(C, k, dilation, c1, c2, &L),
+              DISSC_EUNSUPPORTED, "no fused-pair plan for C=64 kernel_size=%d dilation=%d (odd k, halo <= %d)", k, dilation,
+              kTcHalo);
+  const int Tr = (int)round_up(T, 128), Tp = Tr + 2 * kTcHalo;
+  const size_t f_elems = (size_t)B * (C / 8) * Tr * 8, plane_elems = (size_t)B * (C / 8) * Tp * 8 + 4096;
+  auto pk1 = pack_weights_tc(c1, [=](int n, int ci, int j) { return w1_host[((size_t)n * C + ci) * k + j]; }, &c1.inv_scale);
+  auto pk2 = pack_weights_tc(c2, [=](int n, int ci, int j) { return w2_host[((size_t)n * C + ci) * k + j]; }, &c2.inv_scale);
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    tmp.push_back(d);
+    return d;
+  };
+  auto cleanup = [&]() { for (void* d : tmp) cudaFree(d); };
+  __half* dw1 = (__half*)dalloc(pk1.size() * 2);
+  __half* dw2 = (__half*)dalloc(pk2.size() * 2);
+  float* db = (float*)dalloc((size_t)2 * C * 4);
+  __half* i_hi = (__half*)dalloc(plane_elems * 2);
+  __half* i_lo = (__half*)dalloc(plane_elems * 2);
+  float* f_acc = (float*)dalloc(f_elems * 4);
+  float* f_out = (float*)dalloc(f_elems * 4);
+  __half* o_hi = (__half*)dalloc(plane_elems * 2);
+  __half* o_lo = (__half*)dalloc(plane_elems * 2);
+  if (!dw1 || !dw2 || !db || !i_hi || !i_lo || !f_acc || !f_out || !o_hi || !o_lo) {
+    cleanup();
+    return set_err(DISSC_ENOMEM, "cudaMalloc failed in dissc_resblock_pair_tc");
+  }
+  cudaMemcpyAsync(dw1, pk1.data(), pk1.size() * 2, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dw2, pk2.data(), pk2.size() * 2, cudaMemcpyHostToDevice, st);
+  std::vector<float> bias(2 * C, 0.f);
+  if (b1_host) memcpy(bias.data(), b1_host, C * 4);
+  if (b2_host) memcpy(bias.data() + C, b2_host, C * 4);
+  cudaMemcpyAsync(db, bias.data(), (size_t)2 * C * 4, cudaMemcpyHostToDevice, st);
+  // garbage everywhere first: the kernel must not depend on anything but the zeroed halos / rows past the valid length
+  cudaMemsetAsync(i_hi, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(i_lo, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(f_acc, 0xff, f_elems * 4, st);
+  cudaMemsetAsync(f_out, 0xff, f_elems * 4, st);
+  cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
+  cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
+  const int nb = 148 * 4;
+  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, i_hi, i_lo, lengths, len_mul, B, C, C / 8, T, Tp, 1, 0.1f);
+  int rc = launch_zero_halos(i_hi, i_lo, B * C / 8, Tp, T, st);
+  if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * C / 8, Tp, T, st);
+  if (acc_in) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(acc_in, f_acc, B, C, T, Tr);
+  c1.w = dw1; c2.w = dw2;
+  Pair64Params p{};
+  p.x_hi = i_hi; p.x_lo = i_lo; p.in_inv_slope = 10.0f;
+  p.b1 = db; p.b2 = db + C; p.acc_in = acc_in ? f_acc : nullptr;
+  p.out_f = f_out; p.out_hi = out_planes ? o_hi : nullptr; p.out_lo = out_planes ? o_lo : nullptr;
+  p.lengths = lengths; p.len_mul = len_mul;
+  p.B = B; p.T = T; p.Tp = Tp; p.Tr = Tr; p.halo = kTcHalo;
+  p.div = div; p.plane_slope = plane_slope;
+  if (!rc) rc = launch_pair64(p, L, c1, c2, st);
+  if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, C, T, Tr);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cleanup();
+  if (rc) return rc;
+  DISSC_CUDA(e);
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
+}
+
 }  // namespace dissc
 
 // ------------------------------------------------------------------------
@@ -948,6 +1153,13 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
       for (int m = 0; m < c.n_dil && g->stage_pair[i]; ++m)
         g->stage_pair[i] = pair_plan(c.c0 >> (i + 1), c.rk[j], c.dil[j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1],
                                      &g->rb_pair[i][j][m]);
+    // C = 64: planes-in / planes-out fused pairs with streamed weights (the stage after must not be the last one: its
+    // output goes on as planes)
+    g->stage_pair64[i] = g->tc_all && c.resblock == 1 && !g->stage_pair[i] && (c.c0 >> (i + 1)) == 64 && i + 1 < c.n_up;
+    for (int j = 0; j < c.n_rk && g->stage_pair64[i]; ++j)
+      for (int m = 0; m < c.n_dil && g->stage_pair64[i]; ++m)
+        g->stage_pair64[i] = pair64_plan(64, c.rk[j], c.dil[j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1],
+                                         &g->rb_pair64[i][j][m]);
   }
   // conv_post: (1, ch, 7) -> plain (ch, 7)
   {
@@ -1327,6 +1539,9 @@ int dissc_resblock_pair_tc(const float* in, const float* w1_host, const float* b
                            const int32_t* lengths, int len_mul, int B, int C, int T, int k, int dilation, float div,
                            float plane_slope, void* stream) {
   DISSC_CHECK(in && w1_host && w2_host && B > 0 && C > 0 && T > 0, DISSC_EINVAL, "bad argument");
+  if (C == 64)
+    return pair64_layer_test(in, w1_host, b1_host, w2_host, b2_host, acc_in, out_raw, out_planes, lengths, len_mul, B, T, k,
+                             dilation, div, plane_slope, static_cast<cudaStream_t>(stream));
   TcLayer c1, c2;
   PairLayer L;
   DISSC_CHECK(tc_plan_conv(C, C, k, dilation, &c1) && tc_plan_conv(C, C, k, 1, &c2) && pair_plan(C, k, dilation, c1, c2, &L),

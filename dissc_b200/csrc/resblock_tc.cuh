@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
     unsigned char* xt = sXt + g * xt_bytes;
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * 4u * NC;
     const uint32_t t_acc2 = t_acc1 + 2u * NC;
+    const unsigned r1_magic = 0xFFFFFFFFu / (unsigned)R1 + 1u;   // ceil(2^32 / R1): umulhi(item, magic) == item / R1 for item < 2^16
     // convert: fp32 staging tile -> lrelu -> fp16 hi/lo operand tile (rows outside [0, Tvalid) are zeros)
     auto convert = [&](int tile, uint32_t ph) {
       const int b = tile / p.tiles_per_b;
@@ -212,20 +213,20 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
       mbar_wait(&xop_empty[g], ph ^ 1);
       const int tx0 = t0 - p2 - p1;
       for (int item = wt; item < C8 * R1; item += WPG * 32) {
-        const int c8 = item / R1, i = item - c8 * R1;
+        const int c8 = (int)__umulhi((unsigned)item, r1_magic), i = item - c8 * R1;   // item / R1 (exact: item < 2^16)
         const int t = tx0 + i;
-        float v[8];
         if (t >= 0 && t < Tvalid) {
           const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)item * 32);
           const float4 c = *reinterpret_cast<const float4*>(stg + (size_t)item * 32 + 16);
+          float v[8];
           v[0] = leaky(a.x, 0.1f); v[1] = leaky(a.y, 0.1f); v[2] = leaky(a.z, 0.1f); v[3] = leaky(a.w, 0.1f);
           v[4] = leaky(c.x, 0.1f); v[5] = leaky(c.y, 0.1f); v[6] = leaky(c.z, 0.1f); v[7] = leaky(c.w, 0.1f);
+          split_store8(reinterpret_cast<__half*>(xop + (size_t)item * 16),
+                       reinterpret_cast<__half*>(xop + xop_plane + (size_t)item * 16), v);
         } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          *reinterpret_cast<uint4*>(xop + (size_t)item * 16) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(xop + xop_plane + (size_t)item * 16) = make_uint4(0, 0, 0, 0);
         }
-        split_store8(reinterpret_cast<__half*>(xop + (size_t)item * 16),
-                     reinterpret_cast<__half*>(xop + xop_plane + (size_t)item * 16), v);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -250,12 +251,8 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
           const size_t fi = (((size_t)b * C8 + c8_0 + q) * p.Tpf + p.f_halo + t_out) * 8;
-          rq[2 * q] = *reinterpret_cast<const float4*>(p.x + fi);
-          rq[2 * q + 1] = *reinterpret_cast<const float4*>(p.x + fi + 4);
-          if (p.acc_in) {
-            aq[2 * q] = *reinterpret_cast<const float4*>(p.acc_in + fi);
-            aq[2 * q + 1] = *reinterpret_cast<const float4*>(p.acc_in + fi + 4);
-          }
+          ldg8(p.x + fi, rq[2 * q], rq[2 * q + 1]);
+          if (p.acc_in) ldg8(p.acc_in + fi, aq[2 * q], aq[2 * q + 1]);
         }
       }
       // ---- epilogue 1: acc1 -> xt tile
@@ -274,11 +271,16 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
           const int c8 = c8_0 + q;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = v_ok ? leaky((m[q][e] + x8[q][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f) : 0.f;
           const size_t o = ((size_t)c8 * R2 + row) * 16;
-          split_store8(reinterpret_cast<__half*>(xt + o), reinterpret_cast<__half*>(xt + xt_plane + o), v);
+          if (v_ok) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = leaky((m[q][e] + x8[q][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f);
+            split_store8(reinterpret_cast<__half*>(xt + o), reinterpret_cast<__half*>(xt + xt_plane + o), v);
+          } else {
+            *reinterpret_cast<uint4*>(xt + o) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(xt + xt_plane + o) = make_uint4(0, 0, 0, 0);
+          }
         }
       }
       tc_fence_before();
@@ -321,22 +323,25 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
             for (int e = 0; e < 8; ++e) v[e] = v[e] / p.div;
           }
           if (p.out_f) {
-            float* o = p.out_f + (((size_t)b * C8 + c8) * p.Tpf + p.f_halo + t_out) * 8;
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            stg8(p.out_f + (((size_t)b * C8 + c8) * p.Tpf + p.f_halo + t_out) * 8, v);
           }
           if (p.out_plain) {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              p.out_plain[((size_t)b * NC + c8 * 8 + e) * p.T + t_out] = tc_act(v[e], p.plain_act, p.plain_slope);
+              p.out_plain[((size_t)b * NC + c8 * 8 + e) * p.T + t_out] = p.plain_act ? leaky(v[e], p.plain_slope) : v[e];
           }
         }
         if (p.out_hi) {
-          float a[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) a[e] = out_valid ? tc_act(v[e], p.plane_act, p.plane_slope) : 0.f;
           const size_t o = (((size_t)b * C8 + c8) * p.Tp + p.p_halo + t_out) * 8;
-          split_store8(p.out_hi + o, p.out_lo + o, a);
+          if (out_valid) {
+            float a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] = p.plane_act ? leaky(v[e], p.plane_slope) : v[e];
+            split_store8(p.out_hi + o, p.out_lo + o, a);
+          } else {
+            *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(0, 0, 0, 0);
+          }
         }
       }
     }

@@ -8,9 +8,11 @@ dissc_b200.inference ...`` or a single process), utterances are length-sorted, d
 batches with per-utterance ``lengths`` -- each row equals the reference's B=1 output for that utterance.
 
 The input side keeps only what feeds the Generator (sr/dataset.py:107-122,291-312): units, F0 (speaker-normalised on
-voiced frames iff ``f0_normalize``) and the speaker id.  The reference additionally loads every ground-truth wav and
-computes a mel-spectrogram per item that inference never uses (sr/dataset.py:224-234,269-271) -- not done here, so no
-``_gt.wav`` copies are written.
+voiced frames iff ``f0_normalize``) and the speaker id.  The reference additionally computes a mel-spectrogram per
+item that inference never uses (sr/dataset.py:269-271) -- not done here.  The ground-truth wav is read only to write
+the ``<stem>_gt.wav`` copy (and for the ``--eval_mode`` length clipping); a missing / unreadable file is skipped
+instead of aborting the run.  ``--f0-stats``, ``--unseen-f0``, ``--sample_df`` and ``--code_file`` follow
+sr/inference.py:97-100,122-129,146-147,214-235.
 """
 from __future__ import annotations
 
@@ -125,6 +127,13 @@ def peak_normalize(audio_i16: np.ndarray) -> np.ndarray:
     return x / peak
 
 
+def peak_normalize_f32(x: np.ndarray) -> np.ndarray:
+    """``librosa.util.normalize`` on a float signal (the ground-truth copy, sr/inference.py:255)."""
+    x = np.asarray(x, dtype=np.float32)
+    peak = np.max(np.abs(x)) if x.size else 0.0
+    return x if peak < np.finfo(np.float32).tiny else x / peak
+
+
 def write_wav(path: str, rate: int, audio: np.ndarray) -> None:
     from scipy.io.wavfile import write
     write(path, rate, audio)
@@ -187,6 +196,67 @@ def vocode_items(generator: CodeGenerator, items: List[dict], device, spkr_overr
     return out
 
 
+def rescale_f0(f0: np.ndarray, new_mean: float, new_std: float) -> np.ndarray:
+    """``--f0-stats`` re-scaling of sr/inference.py:220-235: voiced frames are standardised with their OWN mean / std
+    (``torch.std``: unbiased) and moved to the target speaker's statistics; unvoiced frames stay 0."""
+    f0 = torch.from_numpy(np.asarray(f0, dtype=np.float32)).clone()
+    ii = f0 != 0
+    mean_, std_ = f0[ii].mean(), f0[ii].std()
+    f0[ii] -= mean_
+    f0[ii] /= std_
+    f0[ii] *= new_std
+    f0[ii] += new_mean
+    return f0.numpy()
+
+
+def target_f0_stats(f0_stats: dict, spkr: int):
+    """sr/inference.py:227-230: per-speaker entry of the ``--f0-stats`` dict, else its global ``f0_mean`` / ``f0_std``."""
+    if spkr not in f0_stats:
+        return float(f0_stats["f0_mean"]), float(f0_stats["f0_std"])
+    return float(f0_stats[spkr]["f0_mean"]), float(f0_stats[spkr]["f0_std"])
+
+
+def parse_code_file(path: str) -> List[dict]:
+    """``--code_file`` (sr/inference.py:122-129): one ``<name>|<c0 c1 c2 ...>`` line per utterance, units only."""
+    items = []
+    with open(path) as f:
+        for line in f.readlines():
+            x = line.strip().split("|")
+            if len(x) < 2:
+                continue
+            items.append({"name": x[0], "code": np.asarray([int(v) for v in x[1].split(" ") if v], dtype=np.int64)})
+    return items
+
+
+def load_gt_audio(path, sampling_rate: int, pad: Optional[int] = None) -> Optional[np.ndarray]:
+    """Ground-truth audio the way CodeDataset.__getitem__ prepares it (sr/dataset.py:223-234): int16 wav -> optional
+    zero padding to a multiple of ``pad`` -> / 32768 -> peak-normalised * 0.95.  None when the file is missing, is not
+    a PCM wav scipy can read, or has another sampling rate (the reference resamples with resampy, absent here)."""
+    from scipy.io import wavfile
+    try:
+        rate, audio = wavfile.read(str(path))
+    except (OSError, ValueError):
+        return None
+    if rate != sampling_rate:
+        return None
+    if audio.ndim > 1:
+        audio = audio[:, 0]
+    audio = audio.astype(np.float64)
+    if pad:
+        audio = np.pad(audio, (0, pad - (audio.shape[-1] % pad)), "constant", constant_values=0)
+    audio = audio / 32768.0
+    peak = np.max(np.abs(audio)) if audio.size else 0.0
+    if peak >= np.finfo(np.float32).tiny:
+        audio = audio / peak
+    return (audio * 0.95).astype(np.float32)
+
+
+def sample_df_targets(df, out_name: str, spkr_to_id: dict) -> List[int]:
+    """sr/inference.py:214-216: the conversions listed for this sample in the ``--sample_df`` table."""
+    cur_name = out_name.split("_mic2")[0]
+    return [spkr_to_id[i] for i in df[df.syn_sample == cur_name].syn_trgt.unique()]
+
+
 def build_parser():
     """sr/inference.py:263-281."""
     ap = argparse.ArgumentParser()
@@ -211,11 +281,15 @@ def build_parser():
     return ap
 
 
+def _torch_load(path):
+    try:
+        return torch.load(path, map_location="cpu", weights_only=False)
+    except TypeError:  # torch without the weights_only keyword
+        return torch.load(path, map_location="cpu")
+
+
 def main(argv: Optional[Sequence[str]] = None):
     a = build_parser().parse_args(argv)
-    for flag in ("code_file", "f0_stats", "unseen_f0", "sample_df"):
-        if getattr(a, flag):
-            raise NotImplementedError(f"--{flag} is not supported by dissc_b200.inference")
     from . import dist as ddist
     rank, world, local = ddist.init_from_env()
     if not torch.cuda.is_available():
@@ -228,30 +302,70 @@ def main(argv: Optional[Sequence[str]] = None):
         print(f"Didn't find checkpoints for {cp_g}")   # sr/inference.py:307-309
         return
     generator = CodeGenerator(h).to(device)
-    generator.load_state_dict(torch.load(cp_g, map_location="cpu")["generator"])
+    generator.load_state_dict(_torch_load(cp_g)["generator"])
     generator.eval()
     generator.remove_weight_norm()
-    base_path = h.test_base_path if a.data_path is None else a.data_path
-    audio_files, codes, pitch = parse_manifest(a.input_code_file, base_path)
-    spk_pkl = a.id_to_spkr if a.unseen_speaker else f"{os.path.dirname(h.input_training_file)}/id_to_spkr.pkl"
-    with open(spk_pkl, "rb") as f:
-        id_to_spkr = pickle.load(f)
-    f0_stats = None
-    if h.get("f0_stats", None):
-        with open(h.f0_stats, "rb") as f:
-            f0_stats = pickle.load(f)
-    items = prepare_items(h, audio_files, codes, pitch, id_to_spkr, f0_stats, a.unseen_speaker)
-    items = items[: a.n + 1]                                   # reference stops after i > n (sr/inference.py:356-358)
+    os.makedirs(a.output_dir, exist_ok=True)
+
+    df = None
+    if a.sample_df:                                            # sr/inference.py:97-100
+        import pandas as pd
+        df = pd.read_csv(a.sample_df, index_col=0)
+        if a.target_speakers:
+            df = df[df.syn_trgt.isin(a.target_speakers)]
+
+    id_to_spkr: Sequence[str] = []
+    gt_paths: List[Optional[Path]] = []
+    if a.code_file is not None:                                # units only: no F0 / speaker conditioning available
+        if h.get("f0", None) or h.get("multispkr", None):
+            raise NotImplementedError("--code_file carries units only; this checkpoint's config also conditions on "
+                                      "f0 / speaker (the reference crashes on this combination too: parse_code "
+                                      "returns a list, sr/inference.py:125-129,178)")
+        items = parse_code_file(a.code_file)
+        gt_paths = [None] * len(items)
+    else:
+        base_path = h.test_base_path if a.data_path is None else a.data_path
+        audio_files, codes, pitch = parse_manifest(a.input_code_file, base_path)
+        spk_pkl = a.id_to_spkr if a.unseen_speaker else f"{os.path.dirname(h.input_training_file)}/id_to_spkr.pkl"
+        with open(spk_pkl, "rb") as f:
+            id_to_spkr = pickle.load(f)
+        f0_stats = None
+        if a.unseen_f0:                                        # sr/inference.py:146-147
+            f0_stats = _torch_load(a.unseen_f0)
+        elif h.get("f0_stats", None):
+            with open(h.f0_stats, "rb") as f:
+                f0_stats = pickle.load(f)
+        items = prepare_items(h, audio_files, codes, pitch, id_to_spkr, f0_stats, a.unseen_speaker)
+        gt_paths = list(audio_files)
+    items = items[: a.n + 1] if a.n != -1 else items           # reference stops after i > n (sr/inference.py:356-358)
+    gt_paths = gt_paths[: len(items)]
     mine = ddist.shard_by_length([len(it["code"]) for it in items], world)[rank]
     my_items = [items[i] for i in mine]
-    os.makedirs(a.output_dir, exist_ok=True)
+    my_gt = [gt_paths[i] for i in mine]
     spkr_to_id = {k: v for v, k in enumerate(id_to_spkr)}
+    hop = int(h.get("code_hop_size", generator.hop))
 
     def out_name(it):
         p = Path(it["name"])
         return "_".join(p.parts[-3:])[:-4] if a.parts else p.stem
 
-    if not a.unseen_speaker:                                   # resynthesis (sr/inference.py:203-207)
+    # ground truth copies (sr/inference.py:253-256); with --eval_mode (store_false -> not eval) codes / f0 are clipped to
+    # the audio length first (sr/dataset.py:244-252)
+    write_gt = df is None and a.code_file is None
+    gts: List[Optional[np.ndarray]] = [None] * len(my_items)
+    if write_gt or not a.eval_mode:
+        for j, pth in enumerate(my_gt):
+            gts[j] = load_gt_audio(pth, h.sampling_rate, a.pad) if pth is not None else None
+    if not a.eval_mode:
+        for it, gt in zip(my_items, gts):
+            if gt is None:
+                continue
+            n = min(gt.shape[0] // hop, len(it["code"]))
+            it["code"] = it["code"][:n]
+            if "f0" in it:
+                it["f0"] = it["f0"][:n]
+
+    if df is None and not a.unseen_speaker:                    # resynthesis (sr/inference.py:203-207)
         for i, audio in vocode_items(generator, my_items, device, None, a.batch).items():
             write_wav(os.path.join(a.output_dir, out_name(my_items[i]) + "_gen.wav"), h.sampling_rate,
                       peak_normalize(audio))
@@ -261,10 +375,35 @@ def main(argv: Optional[Sequence[str]] = None):
         else:
             random.seed(52 + rank)
             spkrs = random.sample(range(len(id_to_spkr)), k=min(5, len(id_to_spkr)))
-        for k in spkrs:
-            for i, audio in vocode_items(generator, my_items, device, k, a.batch).items():
-                write_wav(os.path.join(a.output_dir, out_name(my_items[i]) + f"_{k}_gen.wav"), h.sampling_rate,
+        per_item = [list(spkrs)] * len(my_items)
+        if df is not None:
+            per_item = [sample_df_targets(df, out_name(it), spkr_to_id) for it in my_items]
+        f0_tgt = None
+        if a.f0_stats and h.get("f0", None) is not None:
+            f0_tgt = _torch_load(a.f0_stats)                   # sr/inference.py:157-158
+        rescale = f0_tgt is not None and not h.get("f0_normalize", False)
+        order: List[int] = []
+        for ks in per_item:
+            for k in ks:
+                if k not in order:
+                    order.append(k)
+        for k in order:
+            sel = [j for j, ks in enumerate(per_item) if k in ks]
+            if rescale:
+                # like the reference, the re-scaled contour REPLACES the item's f0 (code['f0'] = f0, :235), so the next
+                # target speaker standardises the already re-scaled contour
+                for j in sel:
+                    if (my_items[j]["f0"] != 0).any():
+                        my_items[j]["f0"] = rescale_f0(my_items[j]["f0"], *target_f0_stats(f0_tgt, k))
+            sub = [my_items[j] for j in sel]
+            for i, audio in vocode_items(generator, sub, device, k, a.batch).items():
+                write_wav(os.path.join(a.output_dir, out_name(sub[i]) + f"_{k}_gen.wav"), h.sampling_rate,
                           peak_normalize(audio))
+    if write_gt:
+        for it, gt in zip(my_items, gts):
+            if gt is not None:
+                write_wav(os.path.join(a.output_dir, out_name(it) + "_gt.wav"), h.sampling_rate,
+                          peak_normalize_f32(gt))
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -354,7 +354,7 @@ def _pair_case(dev, B, C, T, k, d, acc=False, div=0.0, lengths=None, seed=0):
     assert (pl - F.leaky_relu(want, 0.1)).abs().max().item() < 3e-5
 
 
-@pytest.mark.parametrize("C", [16, 32])
+@pytest.mark.parametrize("C", [16, 32, 64])
 @pytest.mark.parametrize("k,d", [(3, 1), (3, 3), (3, 5), (7, 1), (7, 3), (7, 5), (11, 1), (11, 3), (11, 5)])
 def test_pair_resblock_shapes(cuda_device, C, k, d):
     _pair_case(cuda_device, 2, C, 1000, k, d)
@@ -371,3 +371,18 @@ def test_pair_many_tiles_and_lengths(cuda_device):
     _pair_case(cuda_device, 6, 16, 126 * 160, 3, 1, acc=True)
     _pair_case(cuda_device, 4, 32, 118 * 90 + 5, 11, 5, acc=True, div=3.0)
     _pair_case(cuda_device, 4, 32, 700, 7, 3, lengths=[700, 1, 257, 433])
+
+
+# C = 64: planes in / planes out, streamed weights, residual rebuilt from the planes (resblock64_tc.cuh)
+@pytest.mark.parametrize("T", [1, 2, 117, 118, 119, 128, 1025])
+def test_pair64_ragged_time(cuda_device, T):
+    _pair_case(cuda_device, 2, 64, T, 11, 5)
+    _pair_case(cuda_device, 3, 64, T, 3, 1, acc=True, div=3.0)
+
+
+def test_pair64_many_tiles_and_lengths(cuda_device):
+    # far more tiles than SMs: both worker groups and the weight ring wrap their phases many times
+    _pair_case(cuda_device, 6, 64, 126 * 160, 3, 1, acc=True)
+    _pair_case(cuda_device, 4, 64, 118 * 90 + 5, 11, 5, acc=True, div=3.0)
+    _pair_case(cuda_device, 4, 64, 122 * 77 + 1, 7, 3)
+    _pair_case(cuda_device, 4, 64, 700, 7, 3, lengths=[700, 1, 257, 433])
