@@ -70,6 +70,23 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  Single-thread regions that issue tcgen05.mma / tcgen05.commit / bulk TMA
+// must be entered through this and not through `lane == 0`: the compiler then knows exactly one thread runs the region
+// and emits the uniform-datapath instructions (UTCHMMA, UTCBAR, UBLKCP) back to back; behind a plain divergent branch
+// it wraps EVERY such instruction in an ELECT / BRA.U.ANY waterfall loop (~10 extra instructions per MMA), which made
+// the MMA-issue thread the bottleneck of every N <= 128 layer (profiles/README.md, r01_d).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // leaky-relu for 0 <= slope <= 1 (the reference uses 0.1 and 0.01): max(v, v*slope) is two instructions, bit-identical
 // to the select form for every finite v.
 __device__ __forceinline__ float leaky(float v, float slope) { return fmaxf(v, v * slope); }

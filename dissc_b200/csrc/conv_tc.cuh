@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 
 
   if (warp == 0) {
     // ===================== producer: bulk TMA =====================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t abuf = 0, aph = 0, ws = 0, wph = 0;
       bool first = true;
       const int kb8 = p.KB / 8;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
       constexpr uint32_t idesc_n = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * NC) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kPair64Threads, 1) resblock_pair64_tc_kernel(c
 
   if (warp == 0) {
     // ===================== producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t ws = 0, wph = 0;
       auto load_w = [&](const __half* w) {
         const unsigned char* wb = reinterpret_cast<const unsigned char*>(w);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kPair64Threads, 1) resblock_pair64_tc_kernel(c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_n = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * NC) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lbo_x = (uint32_t)R1 * 16, lbo_t = (uint32_t)R2 * 16;

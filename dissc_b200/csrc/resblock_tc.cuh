@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
 
   if (warp == 0) {
     // ===================== producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(&w_full[0], 2 * w_bytes);
       tma_load_1d(sW1, p.w1, w_bytes, &w_full[0]);
       tma_load_1d(sW2, p.w2, w_bytes, &w_full[0]);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_n = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * NC) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lbo_x = (uint32_t)R1 * 16, lbo_t = (uint32_t)R2 * 16;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive(&xop_full[g]);
         mbar_arrive(&stg_empty[g]);
       }
