@@ -154,7 +154,8 @@ static int launch_convt(const ConvTParams& p, int k, int u, int co_tile, cudaStr
 static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
   if (k != 7) return set_err(DISSC_EUNSUPPORTED, "conv_post kernel_size=%d (only 7)", k);
   if (p.Cin > kPostMaxCin) return set_err(DISSC_EUNSUPPORTED, "conv_post Cin=%d > %d", p.Cin, kPostMaxCin);
-  dim3 grid((p.T + kPostTile - 1) / kPostTile, p.B);
+  const int per_cta = kThreads * kPostRT;
+  dim3 grid((p.T + per_cta - 1) / per_cta, p.B);
   conv_post_kernel<7><<<grid, kThreads, 0, st>>>(p);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;

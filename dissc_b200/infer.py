@@ -82,14 +82,17 @@ def repeat_interleave(dd: torch.Tensor, counts: torch.Tensor, dd_len: torch.Tens
 
 @torch.no_grad()
 def convert_batch(seqs: torch.Tensor, spk_id: torch.Tensor, n_tokens: int, len_model: Optional[LenPredictor] = None,
-                  pitch_model=None, norm_pitch: bool = True, lengths: Optional[torch.Tensor] = None):
-    """Batched ``_infer_sample`` (infer.py:24-45) for the predicted-pitch mode.
+                  pitch_model=None, norm_pitch: bool = True, lengths: Optional[torch.Tensor] = None,
+                  return_lens: bool = False):
+    """Batched ``_infer_sample`` (infer.py:24-45); ``f0`` is None without a pitch model (the caller then interpolates the
+    original contour with ``morph_seq_len``).  ``return_lens`` adds the per-unit predicted lengths (B,Ld) and dd_len.
 
     seqs int64 (B,L) padded with ``n_tokens``; spk_id (B,1) target speakers.
     -> (out_seq int64 (B,L_out) padded with n_tokens, f0 fp32 (B,L_out) or None, out_len int32 (B))."""
     dev = seqs.device
     B = seqs.shape[0]
     dd, counts, dd_len = dedup_units(seqs, n_tokens, lengths)
+    new_counts = counts
     if len_model is not None:
         Ld = max(int(dd_len.max().item()), 1)
         dd_c = dd[:, :Ld].contiguous()
@@ -106,19 +109,52 @@ def convert_batch(seqs: torch.Tensor, spk_id: torch.Tensor, n_tokens: int, len_m
     f0 = None
     if pitch_model is not None:
         f0 = pitch_model.infer_freq(out_seq, spk_id, norm_pitch, lengths=out_len)
+    if return_lens:
+        return out_seq, f0, out_len, new_counts, dd_len
     return out_seq, f0, out_len
+
+
+def interp(vals, target_len: int):
+    """utils.py:39-45: nearest-neighbour resampling of one run's pitch values to ``target_len`` points."""
+    import numpy as np
+    vals = list(vals)
+    cur_len = len(vals)
+    if cur_len == 1:
+        return np.array(int(target_len) * vals)
+    if target_len == cur_len:
+        return np.array(vals)
+    from scipy.interpolate import interp1d
+    return interp1d(np.linspace(0., 1., cur_len), vals, bounds_error=False, kind="nearest", fill_value=0)(
+        np.linspace(0., 1., int(target_len)))
+
+
+def morph_seq_len(units, pitch, t_lens):
+    """utils.py:47-52 -- the heuristic used when the pitch is NOT predicted (``--pred_len`` without ``--pred_pitch``):
+    every run of equal units keeps its own pitch values, stretched / squeezed to the run's predicted length.  Host numpy,
+    exactly as in the reference (a few hundred values per utterance)."""
+    import numpy as np
+    from itertools import groupby
+    out = []
+    for i, (_, g) in enumerate(groupby(zip(units, pitch), key=lambda x: x[0])):
+        out.append(interp([f for _, f in g], int(t_lens[i])))
+    return np.concatenate(out) if out else np.zeros((0,))
 
 
 def infer_sample(seqs, pitch, spk_id, name, out_path, len_model=None, pitch_model=None, norm_pitch=False, n_tokens=100):
     """Signature-compatible ``_infer_sample`` (infer.py:24-45), B=1: appends one JSON line to ``out_path``.
-    The heuristic ``morph_seq_len`` mode (no pitch model, utils.py:47-52) is CPU numpy in the reference and is not part
-    of this GPU path."""
-    if pitch_model is None:
-        raise NotImplementedError("pitch interpolation without a pitch model (utils.morph_seq_len) is host-only numpy in "
-                                  "the reference and is not implemented here; pass --pred_pitch")
-    out_seq, f0, out_len = convert_batch(seqs.view(1, -1), spk_id.view(1, 1), n_tokens, len_model, pitch_model, norm_pitch)
+    Without a pitch model the original ``pitch`` contour is morphed to the predicted run lengths (utils.morph_seq_len)."""
+    out_seq, f0, out_len, new_counts, dd_len = convert_batch(seqs.view(1, -1), spk_id.view(1, 1), n_tokens, len_model,
+                                                             pitch_model, norm_pitch, return_lens=True)
     n = int(out_len[0].item())
-    out = {"units": out_seq[0, :n].cpu().numpy().tolist(), "f0": f0[0, :n].cpu().numpy().tolist(), "audio": name}
+    units = out_seq[0, :n].cpu().numpy().tolist()
+    if pitch_model is not None:
+        pitches = f0[0, :n].cpu().numpy().tolist()
+    else:
+        in_seq = seqs.view(-1)
+        in_seq = in_seq[in_seq != n_tokens].cpu().numpy()
+        pitches = morph_seq_len(in_seq, torch.as_tensor(pitch).cpu().numpy(),
+                                new_counts[0, :int(dd_len[0])].cpu().numpy()).tolist()
+    out = {"units": units, "f0": pitches, "audio": name}
     with open(out_path, "a+") as f:
         f.write(f"{json.dumps(out)}\n")
     return out
@@ -177,38 +213,72 @@ def run(args, batch_size: int = 256):
     rows = [parse_line(l) for l in open(args.input_path) if l.strip()]
     if not args.wild_sample:
         rows = rows[:args.n]
+    df = None
+    if args.sample_df and not args.wild_sample:                # infer.py:50-51
+        import pandas as pd
+        df = pd.read_csv(args.sample_df, index_col=0)
+    vc_targets: List[str] = []
+    if args.wild_sample:
+        vc_targets = list(args.target_speakers or [])
+    elif args.vc:                                              # infer.py:87-92
+        if args.target_speakers:
+            vc_targets = list(args.target_speakers)
+        else:
+            import random
+            vc_targets = random.sample(list(spk_id_dict.keys()), k=min(1, len(spk_id_dict)))
     targets: List[Optional[str]] = []
-    if not args.wild_sample and not args.sample_df:
+    if not args.wild_sample and df is None:
         targets.append(None)                       # reconstruction with the source speaker (infer.py:113)
-    if args.vc or args.wild_sample:
-        targets += list(args.target_speakers or [])
-    for t in targets:
+    targets += vc_targets
+    if df is not None and vc_targets:              # only the conversions the table lists per sample (infer.py:118-119)
+        per_row = [set(df[df.syn_sample == os.path.splitext(r["audio"])[0].split("_mic2")[0]].syn_trgt.unique())
+                   for r in rows]
+        targets = sorted({t for ts in per_row for t in ts}, key=str)
+    else:
+        per_row = None
+    for t in set(targets) | set(vc_targets):
         p = f"{args.out_path}/{base}" if t is None else f"{args.out_path}/{t}_{base}"
         if os.path.exists(p):
             os.remove(p)
-    for i0 in range(0, len(rows), batch_size):
-        chunk = rows[i0:i0 + batch_size]
-        L = max(len(r["units"]) for r in chunk)
-        seqs = torch.full((len(chunk), L), args.n_tokens, dtype=torch.int64)
-        for b, r in enumerate(chunk):
-            seqs[b, :len(r["units"])] = torch.as_tensor(r["units"], dtype=torch.int64)
-        seqs = seqs.to(device)
-        for t in targets:
+    morph = pitch_model is None                    # infer.py:39-40: interpolate the original contour heuristically
+    for t in targets:
+        sel = list(range(len(rows))) if per_row is None else [i for i in range(len(rows)) if t in per_row[i]]
+        p = f"{args.out_path}/{base}" if t is None else f"{args.out_path}/{t}_{base}"
+        for i0 in range(0, len(sel), batch_size):
+            chunk = [rows[i] for i in sel[i0:i0 + batch_size]]
+            L = max(len(r["units"]) for r in chunk)
+            seqs = torch.full((len(chunk), L), args.n_tokens, dtype=torch.int64)
+            for b, r in enumerate(chunk):
+                seqs[b, :len(r["units"])] = torch.as_tensor(r["units"], dtype=torch.int64)
+            seqs = seqs.to(device)
+            src_ids = None
+            if not args.wild_sample:
+                src_ids = [spk_id_dict[r["audio"].split("_")[0]] for r in chunk]
             if t is None:
-                spk = torch.tensor([[spk_id_dict[r["audio"].split("_")[0]]] for r in chunk], device=device)
+                spk = torch.tensor([[i] for i in src_ids], device=device)
             else:
                 spk = torch.full((len(chunk), 1), spk_id_dict[t], device=device)
-            out_seq, f0, out_len = convert_batch(seqs, spk, args.n_tokens, len_model, pitch_model, args.norm_pitch)
+            out_seq, f0, out_len, new_counts, dd_len = convert_batch(seqs, spk, args.n_tokens, len_model, pitch_model,
+                                                                     args.norm_pitch, return_lens=True)
             out_seq, out_len = out_seq.cpu(), out_len.cpu()
             f0 = None if f0 is None else f0.cpu()
-            p = f"{args.out_path}/{base}" if t is None else f"{args.out_path}/{t}_{base}"
+            if morph:
+                new_counts, dd_len = new_counts.cpu().numpy(), dd_len.cpu().numpy()
             with open(p, "a+") as f:
                 for b, r in enumerate(chunk):
                     n = int(out_len[b])
-                    if f0 is None:
-                        raise NotImplementedError("--pred_pitch is required (morph_seq_len is host-only in the reference)")
-                    f.write(json.dumps({"units": out_seq[b, :n].tolist(), "f0": f0[b, :n].tolist(),
-                                        "audio": r["audio"]}) + "\n")
+                    if not morph:
+                        pitches = f0[b, :n].tolist()
+                    else:
+                        # the ORIGINAL contour, normalised with the SOURCE speaker's statistics (infer.py:104-108: done
+                        # before spk_id is overwritten with the target), stretched per run (utils.morph_seq_len)
+                        pitch = torch.tensor(r["f0"], dtype=torch.float32)
+                        if args.norm_pitch:
+                            ii = pitch != 0
+                            pitch[ii] -= mean[src_ids[b]]
+                            pitch[ii] /= std[src_ids[b]]
+                        pitches = morph_seq_len(r["units"], pitch.numpy(), new_counts[b, :int(dd_len[b])]).tolist()
+                    f.write(json.dumps({"units": out_seq[b, :n].tolist(), "f0": pitches, "audio": r["audio"]}) + "\n")
 
 
 def build_parser():
@@ -240,8 +310,6 @@ def main(argv: Optional[Sequence[str]] = None):
     assert args.pred_len | args.pred_pitch, "Inference must at least convert pitch or rhythm (or both)"
     assert (args.wild_sample & args.pred_len & args.pred_pitch) | (not args.wild_sample), \
         "If we use an unknown speaker we must convert both pitch and rhythm"
-    if args.sample_df:
-        raise NotImplementedError("--sample_df (per-sample conversion table) is not supported")
     torch.manual_seed(args.seed if args.seed >= 0 else 0)
     run(args)
 

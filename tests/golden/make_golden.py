@@ -113,9 +113,36 @@ def gen_carryover():
     print("carryover", len(cases))
 
 
+def gen_morph():
+    """utils.morph_seq_len (the no-pitch-prediction path of infer.py:39-40) on seeded run-length sequences."""
+    inf = _refimport.infer_module()          # `from utils import seed_everything, morph_seq_len` (infer.py:20)
+    rng = np.random.RandomState(5)
+    out = {}
+    for i in range(6):
+        n_runs = [1, 2, 5, 17, 40, 3][i]
+        runs = rng.randint(1, 6, size=n_runs)
+        toks = []
+        prev = -1
+        for _ in range(n_runs):
+            t = rng.randint(0, 100)
+            while t == prev:
+                t = rng.randint(0, 100)
+            toks.append(t)
+            prev = t
+        units = np.repeat(np.array(toks), runs)
+        pitch = (100 + 50 * rng.rand(len(units))).astype(np.float32)
+        pitch[rng.rand(len(units)) < 0.3] = 0.0
+        t_lens = rng.randint(1, 8, size=n_runs)
+        res = inf.morph_seq_len(units, pitch, t_lens)
+        out[f"units{i}"], out[f"pitch{i}"], out[f"lens{i}"], out[f"out{i}"] = units, pitch, t_lens, np.asarray(res)
+    np.savez_compressed(os.path.join(HERE, "morph_seq_len.npz"), **out)
+    print("morph", 6)
+
+
 if __name__ == "__main__":
     assert _refimport.available(), "reference tree not found"
     gen_tiny()
     gen_vctk()
     gen_predictors()
     gen_carryover()
+    gen_morph()

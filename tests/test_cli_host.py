@@ -67,3 +67,57 @@ def test_cli_parsers_keep_reference_flags():
     assert a.eval_mode is True and a.n == 2508 and a.target_speakers == ["p231", "p239"]
     p = pinf.build_parser().parse_args(["--pred_len", "--pred_pitch", "--vc", "--target_speakers", "p231"])
     assert p.norm_pitch is True and p.n == 10 and p.f0_model_type == "new" and p.n_tokens == 100
+
+
+# ---------------------------------------------------------------------------------------------
+# flags ported later: --f0-stats, --sample_df, --code_file, _gt.wav (sr/inference.py), morph_seq_len / --sample_df (infer.py)
+# ---------------------------------------------------------------------------------------------
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_morph_seq_len_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "morph_seq_len.npz"))
+    n = len([k for k in g.files if k.startswith("out")])
+    assert n >= 6
+    for i in range(n):
+        got = pinf.morph_seq_len(g[f"units{i}"], g[f"pitch{i}"], g[f"lens{i}"])
+        assert got.shape == g[f"out{i}"].shape
+        assert np.array_equal(np.asarray(got, dtype=np.float64), np.asarray(g[f"out{i}"], dtype=np.float64))
+
+
+def test_rescale_f0_follows_reference_arithmetic():
+    # sr/inference.py:220-235 restated with torch ops on a (1,1,T) tensor, as the reference holds it
+    import torch
+    f0 = torch.tensor([[[0.0, 110.0, 0.0, 130.0, 90.0, 0.0, 100.0]]])
+    ref = f0.clone()
+    ii = ref != 0
+    mean_, std_ = ref[ii].mean(), ref[ii].std()
+    ref[ii] -= mean_
+    ref[ii] /= std_
+    ref[ii] *= 21.0
+    ref[ii] += 185.0
+    got = inf.rescale_f0(f0.view(-1).numpy(), 185.0, 21.0)
+    assert np.array_equal(got, ref.view(-1).numpy())
+    stats = {3: {"f0_mean": 200.0, "f0_std": 30.0}, "f0_mean": 150.0, "f0_std": 25.0}
+    assert inf.target_f0_stats(stats, 3) == (200.0, 30.0) and inf.target_f0_stats(stats, 7) == (150.0, 25.0)
+
+
+def test_code_file_sample_df_and_gt_audio(tmp_path):
+    cf = tmp_path / "codes.txt"
+    cf.write_text("utt_a|1 2 3 3\nutt_b|7\n\n")
+    items = inf.parse_code_file(str(cf))
+    assert [it["name"] for it in items] == ["utt_a", "utt_b"] and items[0]["code"].tolist() == [1, 2, 3, 3]
+    import pandas as pd
+    df = pd.DataFrame({"syn_sample": ["p225_001", "p225_001", "p226_002"], "syn_trgt": ["p231", "p239", "p231"]})
+    spk = {"p225": 0, "p231": 1, "p239": 2}
+    assert inf.sample_df_targets(df, "p225_001_mic2", spk) == [1, 2]
+    assert inf.sample_df_targets(df, "p999_001_mic2", spk) == []
+    from scipy.io import wavfile
+    x = (np.array([0, 1000, -2000, 500], dtype=np.int16))
+    wavfile.write(str(tmp_path / "a.wav"), 16000, x)
+    gt = inf.load_gt_audio(tmp_path / "a.wav", 16000, pad=8)
+    assert gt.shape == (8,) and gt.dtype == np.float32                  # padded to a multiple of `pad`
+    assert np.allclose(gt[:4], 0.95 * x / 2000.0) and np.all(gt[4:] == 0)
+    assert inf.load_gt_audio(tmp_path / "a.wav", 22050) is None          # other rate: skipped (resampy absent)
+    assert inf.load_gt_audio(tmp_path / "missing.wav", 16000) is None
+    assert np.allclose(inf.peak_normalize_f32(gt)[:4], x / 2000.0)
