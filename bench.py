@@ -228,7 +228,7 @@ def main():
     fam = {}
     for name, ms, fl, by in rows:
         key = "conv_tc_kernel" if name.endswith(".tc") else "resblock_pair_tc_kernel" if name.endswith(".ptc") \
-            else "conv_post_kernel" if name == "conv_post" \
+            else "resblock_pair64_tc_kernel" if name.endswith(".p64") else "conv_post_kernel" if name == "conv_post" \
             else "convt1d_kernel" if name.startswith("ups") else "tc_embed_planes+tc_zero_halos" \
             if name in ("embed", "zero_halos") else "conv1d_fused_kernel"
         a = fam.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
@@ -245,7 +245,7 @@ def main():
         del a["flops"], a["bytes"]
     dom_name = max(fam, key=lambda k: fam[k]["ms"])
     dom = fam[dom_name]
-    sfx = {"conv_tc_kernel": ".tc", "resblock_pair_tc_kernel": ".ptc"}.get(dom_name, "")
+    sfx = {"conv_tc_kernel": ".tc", "resblock_pair_tc_kernel": ".ptc", "resblock_pair64_tc_kernel": ".p64"}.get(dom_name, "")
     dom_rows = [r for r in rows if r[0].endswith(sfx)]
     dom_bytes = sum(r[3] for r in dom_rows)
     dom_ms = sum(r[1] for r in dom_rows)
@@ -253,6 +253,14 @@ def main():
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
     fwd_ach = abytes / (ms_step * 1e-3) / 1e9
     split_tflops = 3.0 * dom_flops / (dom_ms * 1e-3) / 1e12   # three fp16 MMAs per fp32-accurate product
+    # measured DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel, from the
+    # committed ncu launch list of the same workload (scripts/ncu_traffic.py); null for other batch shapes
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_d_traffic.json")
+    if (B, T) == (B_PER_GPU, T_UNITS) and os.path.isfile(tpath):
+        tk = json.load(open(tpath))["kernels"].get(dom_name)
+        if tk and tk["launches"] == len(dom_rows):
+            traffic, traffic_src = tk["dram_bytes_per_launch"], "profiles/r01_d_traffic.json (ncu, one forward)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -269,15 +277,16 @@ def main():
                 "bit_identical_to_device_path": parity_e2e},
         "gpu_launches": gen.launches_per_forward() * args.steps,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": f"{dom_name} ({dom['launches']} of {len(rows)} launches per forward, "
                                f"{100 * dom['share']:.1f}% of the step)",
                      "algorithmic_bytes_per_launch_avg": dom_bytes / max(1, len(dom_rows)),
                      "launch_ms_avg": dom_ms / max(1, len(dom_rows)),
                      "forward": {"achieved": fwd_ach, "frac": fwd_ach / peak_gbs, "algorithmic_bytes_per_step": abytes,
                                  "note": "whole step over the timed region (all kernels)"},
-                     "binding_roof": "tensor pipe for stages 0-2 (dense contraction, 85 FLOP/B), HBM/latency for "
-                                     "stages 3-4: see tensor_pipe",
+                     "binding_roof": "tensor pipe (dense contraction, 85 FLOP/B; ncu: tensor pipe 83-94% busy in the "
+                                     "k>=7 layers of every stage): see tensor_pipe; measured DRAM traffic of a "
+                                     "forward is 39.9 GB (algorithmic 72.4 GB)",
                      "tensor_pipe": {"achieved_tflops_fp32_equivalent": dom_flops / (dom_ms * 1e-3) / 1e12,
                                      "achieved_tflops_fp16_mma": split_tflops, "peak_tflops": tensor_peak,
                                      "frac": split_tflops / tensor_peak,

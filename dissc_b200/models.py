@@ -274,14 +274,16 @@ class CodeGenerator(nn.Module):
         _lib.check(_lib.lib().dissc_gen_workspace_bytes(self._ensure_handle(device), B, T, ctypes.byref(n)))
         return n.value
 
-    def _run(self, code, f0, spkr, lengths, B, T, out_dtype):
+    def _run(self, code, f0, spkr, lengths, B, T, out_dtype, ws=None):
         dev = code.device
         L = _lib.lib()
         h = self._ensure_handle(dev)
         need = self.workspace_bytes(B, T, dev)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        if ws is None:
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws = self._ws
         t_out = T
         for u, k in zip(self.rates, self.up_kernels):
             t_out = (t_out - 1) * u - 2 * ((k - u) // 2) + k
@@ -290,9 +292,36 @@ class CodeGenerator(nn.Module):
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             fn = L.dissc_gen_forward if out_dtype == torch.float32 else L.dissc_gen_forward_i16
-            _lib.check(fn(h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T, ptr(out), ptr(self._ws),
-                          self._ws.numel(), stream), "dissc_gen_forward")
+            _lib.check(fn(h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T, ptr(out), ptr(ws), ws.numel(), stream),
+                       "dissc_gen_forward")
         return out
+
+    def capture_graph(self, B: int, T: int, device, int16: bool = False, varlen: bool = False):
+        """CUDA-graph one (B, T) forward: the ~76 kernel launches are captured once and replayed with a single
+        cudaGraphLaunch, which removes the per-launch CPU / driver latency that dominates the reference's own use case
+        (batch size 1, sr/inference.py:178,247).  Returns a ``GraphedForward``: write the static input tensors
+        (``.code`` int64 (B,T), ``.f0`` fp32 (B,T), ``.spkr`` int64 (B), ``.lengths`` int32 (B) if ``varlen``), call it,
+        read ``.out`` ((B, hop*T) fp32 or int16).  Same kernels, same arithmetic: bit-identical to the eager call."""
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        g = GraphedForward()
+        g.code = torch.zeros((B, T), dtype=torch.int64, device=dev)
+        g.f0 = torch.zeros((B, T), dtype=torch.float32, device=dev) if self.f0 else None
+        g.spkr = torch.zeros((B,), dtype=torch.int64, device=dev) if self.multispkr else None
+        g.lengths = torch.full((B,), T, dtype=torch.int32, device=dev) if varlen else None
+        dt = torch.int16 if int16 else torch.float32
+        g.ws = torch.empty(self.workspace_bytes(B, T, dev), dtype=torch.uint8, device=dev)   # owned by the graph
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):   # warm-up outside the capture: handle, workspace, one-time function attributes
+                self._run(g.code, g.f0, g.spkr, g.lengths, B, T, out_dtype=dt, ws=g.ws)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g.graph):
+            g.out = self._run(g.code, g.f0, g.spkr, g.lengths, B, T, out_dtype=dt, ws=g.ws)
+        g._owner = self   # keeps the device handle (weights) alive
+        return g
 
     def forward_host(self, code, f0, spkr, lengths=None, out=None, int16=False, device=0):
         """End-to-end C-ABI call with HOST (ideally pinned) tensors: H2D + forward + D2H + sync."""
@@ -350,3 +379,21 @@ class CodeGenerator(nn.Module):
             _lib.check(L.dissc_gen_profile(h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T, ptr(out), ptr(ws),
                                            need, names, ms, fl, by, cap, ctypes.byref(n)), "dissc_gen_profile")
         return [(names[i].value.decode(), ms[i], fl[i], by[i]) for i in range(n.value)]
+
+
+class GraphedForward:
+    """A captured (B, T) forward (``CodeGenerator.capture_graph``): static inputs ``code`` / ``f0`` / ``spkr`` /
+    ``lengths``, static output ``out``; ``__call__`` replays the graph on the current stream and returns ``out``."""
+    code = f0 = spkr = lengths = out = graph = None
+
+    def __call__(self, code=None, f0=None, spkr=None, lengths=None):
+        if code is not None:
+            self.code.copy_(code.reshape(self.code.shape))
+        if f0 is not None and self.f0 is not None:
+            self.f0.copy_(f0.reshape(self.f0.shape))
+        if spkr is not None and self.spkr is not None:
+            self.spkr.copy_(spkr.reshape(self.spkr.shape))
+        if lengths is not None and self.lengths is not None:
+            self.lengths.copy_(lengths.reshape(self.lengths.shape))
+        self.graph.replay()
+        return self.out

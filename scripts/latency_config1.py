@@ -1,5 +1,5 @@
 """BASELINE configs[0]: one utterance of 50 units (16 000 samples), Generator forward only -- latency on the GPU
-(eager launches) next to the oracle port on the host.   python scripts/latency_config1.py"""
+(eager launches and one CUDA-graph replay) next to the oracle port on the host.   python scripts/latency_config1.py"""
 import os
 import sys
 import time
@@ -32,6 +32,15 @@ def main():
             y = gen(code=c, f0=f, spkr=s)
         torch.cuda.synchronize()
         gpu_ms = (time.perf_counter() - t0) / n * 1e3
+        gf = gen.capture_graph(B, T, dev)
+        yg = gf(code=c, f0=f, spkr=s)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(yg.view(-1), y.view(-1)))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            gf()
+        torch.cuda.synchronize()
+        graph_ms = (time.perf_counter() - t0) / n * 1e3
         fsd = go.folded_state_dict(sd)
         go.code_generator_forward(fsd, cfg, code, f0, spkr)
         t0 = time.perf_counter()
@@ -39,7 +48,7 @@ def main():
             ref = go.code_generator_forward(fsd, cfg, code, f0, spkr)
         cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
         err = (y.cpu() - ref).abs().max().item()
-        print(f"B={B} T={T}: gpu {gpu_ms:.3f} ms ({B * T * 320 / gpu_ms / 1e3:.2f} M samples/s, {gen.launches_per_forward()} launches)"
+        print(f"B={B} T={T}: CUDA graph {graph_ms:.3f} ms (bit-identical to eager: {same}) | eager gpu {gpu_ms:.3f} ms ({B * T * 320 / gpu_ms / 1e3:.2f} M samples/s, {gen.launches_per_forward()} launches)"
               f" | cpu oracle {cpu_ms:.1f} ms ({torch.get_num_threads()} threads) | speed-up {cpu_ms / gpu_ms:.0f}x | max-abs err {err:.1e}")
 
 

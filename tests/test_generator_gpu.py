@@ -140,3 +140,28 @@ def test_rejects_what_it_does_not_implement(cuda_device, vctk_gen):
     g2 = make_generator(bad, syn.synthetic_generator_state_dict(bad, seed=1), cuda_device)
     with pytest.raises(_lib.DisscError, match="kernel_size=9"):
         g2(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+
+
+def test_cuda_graph_replay_is_bit_identical(cuda_device):
+    """CodeGenerator.capture_graph: one cudaGraphLaunch per forward (the B=1 latency case), same kernels -> same bits;
+    new inputs written into the static buffers are picked up by the replay."""
+    from dissc_b200 import AttrDict, CodeGenerator
+    from dissc_b200 import synthetic as syn
+    gen = CodeGenerator(AttrDict(syn.VCTK_CONFIG)).to(cuda_device)
+    gen.load_state_dict(syn.synthetic_generator_state_dict(syn.VCTK_CONFIG, seed=0))
+    gen.eval()
+    gen.remove_weight_norm()
+    gf = gen.capture_graph(2, 37, cuda_device)
+    for seed in (1, 2):
+        code, f0, spkr = (t.to(cuda_device) for t in syn.synthetic_inputs(2, 37, seed=seed))
+        want = gen(code=code, f0=f0, spkr=spkr)
+        got = gf(code=code, f0=f0, spkr=spkr)
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(-1), want.view(-1))
+    gi = gen.capture_graph(1, 50, cuda_device, int16=True, varlen=True)
+    code, f0, spkr = (t.to(cuda_device) for t in syn.synthetic_inputs(1, 50, seed=3))
+    lengths = torch.tensor([41], dtype=torch.int32, device=cuda_device)
+    want = gen.generate_int16(code, f0, spkr, lengths=lengths)
+    got = gi(code=code, f0=f0, spkr=spkr, lengths=lengths)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.int16 and torch.equal(got, want)
