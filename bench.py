@@ -146,7 +146,21 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: dissc_b200 has no CPU path")
-    rank, world, local = ddist.init_from_env()
+    # NCCL may print its version banner on stdout when the first communicator is created: keep stdout to the ONE JSON
+    # line by pointing fd 1 at stderr until the communicator exists
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, world, local = ddist.init_from_env()
+        if world > 1:
+            torch.cuda.set_device(local)
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     dev = torch.device("cuda", local)
