@@ -85,6 +85,8 @@ struct TcParams {
   int groups;            // grouped conv: chunk g reads channel blocks [g*n_cb, (g+1)*n_cb) and writes group_c8 8-channel
   int group_c8;          //   groups of output channels starting at g*group_c8 (NC >= 8*group_c8, padded columns dropped)
   int cout_log2;         // log2(Cout) when Cout is a power of two, else -1 (kTcUp needs it)
+  int cb_split, k_hi;    // channel blocks >= cb_split carry only their first k_hi taps (the others are structural zeros:
+                         //   the odd phase of a stride-2 conv in frame form); cb_split == 0: every block has k taps
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -333,8 +335,9 @@ __global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 
           mbar_wait(&a_full[abuf], aph);
           const uint32_t a_desc0 = umma_desc_lo(sA0 + abuf * a_bytes, lbo_a);
           int j0 = 0;
+          const int kc = (p.cb_split && cb >= p.cb_split) ? p.k_hi : p.k;   // taps with non-zero weights in this block
           for (int g = 0; g < p.SPC; ++g, j0 += p.JG) {
-            const int nt = min(p.JG, p.k - j0);
+            const int nt = min(p.JG, kc - j0);   // <= 0: the stage is only waited for and released
             const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
             if (!p.resident)
               mbar_wait(&w_full[slot], wph);

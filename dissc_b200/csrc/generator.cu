@@ -316,6 +316,7 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale;
   p.Cin8 = L.cin8_total ? L.cin8_total : L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
   p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
+  p.cb_split = L.cb_split; p.k_hi = L.k_hi;
   p.cout_log2 = -1;
   for (int s = 3; s < 12; ++s)
     if ((1 << s) == L.Cout) p.cout_log2 = s;

@@ -629,6 +629,12 @@ int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const
     const int taps = (k + 1) / 2;
     if (!tc_plan(2 * C, C, taps, 1, 0, L, kHubHalo)) return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for extractor conv %d", l));
     L->Cout = C;
+    if (k & 1) {
+      // odd kernel: the last tap of the odd phase (jj = k) does not exist -> the second half of the channel blocks has
+      // one tap less; the MMA thread skips those all-zero steps (1/4 of the layer's MMAs for k = 3)
+      L->cb_split = L->n_cb / 2;
+      L->k_hi = taps - 1;
+    }
     const float* wd = w->data;
     // frame form of a stride-2 conv: channel ci' = phase*C + ci of frame q is x[ci, 2q + phase]; tap j' reads frame q + j'
     auto packed = pack_weights_tc(*L, [=](int n, int cip, int jp) {
