@@ -87,6 +87,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still draining: its prologue (barrier init, TMEM allocation, bias staging) then
+// overlaps the predecessor's tail.  pdl_wait() blocks until the predecessor grid has completed and its writes are
+// visible -- it must precede EVERY global-memory access that depends on (or could overwrite data read by) the
+// predecessor; pdl_launch_dependents() lets the successor start launching.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // leaky-relu for 0 <= slope <= 1 (the reference uses 0.1 and 0.01): max(v, v*slope) is two instructions, bit-identical
 // to the select form for every finite v.
 __device__ __forceinline__ float leaky(float v, float slope) { return fmaxf(v, v * slope); }

@@ -267,6 +267,8 @@ __global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();                 // the prologue above touched only weights / shared memory; activations from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== producer: bulk TMA =====================

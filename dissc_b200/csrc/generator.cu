@@ -261,6 +261,28 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL, common.cuh): only for kernels that call pdl_wait()
+// before their first dependent global access.  DISSC_PDL=0 falls back to ordinary launches.
+static int g_pdl = -1;
+template <typename P>
+static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem, cudaStream_t st, const P& p) {
+  if (g_pdl < 0) {
+    const char* e = getenv("DISSC_PDL");
+    g_pdl = e ? (atoi(e) != 0) : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <int NC, int EPW, int MODE>
 static int launch_conv_tc_inst(const TcParams& p, const TcLayer& L, int grid, cudaStream_t st) {
   static bool attr_set = false;
@@ -269,7 +291,7 @@ static int launch_conv_tc_inst(const TcParams& p, const TcLayer& L, int grid, cu
                                     (int)(kSmemPerSm - 1024)));
     attr_set = true;
   }
-  conv_tc_kernel<NC, EPW, MODE><<<grid, 64 + EPW * 32, L.smem, st>>>(p);
+  DISSC_CUDA(launch_pdl(conv_tc_kernel<NC, EPW, MODE>, grid, 64 + EPW * 32, L.smem, st, p));
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
@@ -392,7 +414,7 @@ static int launch_pair_nc(const PairParams& p, const PairLayer& L, int grid, cud
                                     (int)(kSmemPerSm - 1024)));
     attr_set = true;
   }
-  resblock_pair_tc_kernel<NC><<<grid, PairCfg<NC>::THREADS, L.smem, st>>>(p);
+  DISSC_CUDA(launch_pdl(resblock_pair_tc_kernel<NC>, grid, PairCfg<NC>::THREADS, L.smem, st, p));
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
@@ -459,7 +481,7 @@ static int launch_pair64(Pair64Params p, const Pair64Layer& L, const TcLayer& c1
   p.tiles_per_b = (p.T + m_out - 1) / m_out;
   p.n_tiles = p.B * p.tiles_per_b;
   const int grid = std::min(p.n_tiles, num_sms());
-  resblock_pair64_tc_kernel<<<grid, kPair64Threads, L.smem, st>>>(p);
+  DISSC_CUDA(launch_pdl(resblock_pair64_tc_kernel, grid, kPair64Threads, L.smem, st, p));
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }

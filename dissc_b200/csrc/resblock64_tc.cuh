@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(kPair64Threads, 1) resblock_pair64_tc_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();                 // the prologue above touched only weights / shared memory; activations from here on
+  pdl_launch_dependents();
   // TMEM columns: group g: acc1 at g*256 (main | cross), acc2 at g*256 + 128
 
   int n_mine = 0;

@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();                 // the prologue above touched only weights / shared memory; activations from here on
+  pdl_launch_dependents();
   // TMEM columns: group g: acc1 at g*4NC (main | cross), acc2 at g*4NC + 2NC
 
   if (warp == 0) {
