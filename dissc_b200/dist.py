@@ -85,6 +85,15 @@ class ShardedBatch:
         """-> on rank 0 the (world*B_local, ...) tensor, None elsewhere."""
         if self.world == 1:
             return y_local
-        bufs = [torch.empty_like(y_local) for _ in range(self.world)] if self.rank == 0 else None
-        dist.gather(y_local, bufs, dst=0)
-        return torch.cat(bufs, dim=0) if self.rank == 0 else None
+        # NCCL has no 16-bit integer type ("Unconvertible NCCL type Short"): int16 waveforms travel as raw bytes
+        dtype = y_local.dtype
+        raw = dtype in (torch.int16, torch.uint16)
+        y = y_local.contiguous()
+        if raw:
+            y = y.view(torch.uint8)
+        bufs = [torch.empty_like(y) for _ in range(self.world)] if self.rank == 0 else None
+        dist.gather(y, bufs, dst=0)
+        if self.rank != 0:
+            return None
+        out = torch.cat(bufs, dim=0)
+        return out.view(dtype) if raw else out

@@ -118,6 +118,30 @@ def main():
                           "utterances_per_s": world * B / ms3 * 1e3, "samples_per_s": world * n3 / ms3 * 1e3,
                           "samples_vocoded_per_gpu_step": n3, "mean_output_frames": n3 / gen.hop / B}))
 
+    # ---- rank 0 owns inputs and outputs: NCCL scatter of (code, f0, spkr, lengths) -> local vocode -> NCCL gather of the
+    #      int16 waveforms (replaces the reference's Pool(8) + files on disk, sr/inference.py:351-359)
+    sb = ddist.ShardedBatch(rank, world, dev)
+    Bl, Tg = 64, 300
+    if rank == 0:
+        cg, fg, sg = syn.synthetic_inputs(world * Bl, Tg, seed=99)
+        cg, fg, sg = cg.to(dev), fg.reshape(world * Bl, Tg).to(dev), sg.reshape(world * Bl).to(dev)
+        lg = torch.full((world * Bl,), Tg, dtype=torch.int32, device=dev)
+    else:
+        cg = fg = sg = lg = None
+
+    def scatter_vocode_gather():
+        c, f, s_, l_ = sb.scatter(cg, fg, sg, lg, Bl, Tg)
+        y = gen.generate_int16(c, f, s_, lengths=l_)
+        return sb.gather(y)
+
+    msg, yg = timed(scatter_vocode_gather, a.iters, dev)
+    msg = mx(msg)
+    if rank == 0:
+        print(json.dumps({"config": "2 with rank 0 owning inputs/outputs: NCCL scatter -> vocode -> NCCL gather (int16)",
+                          "n_gpus": world, "utterances": world * Bl, "units": Tg, "ms_per_step": msg,
+                          "samples_per_s": world * Bl * Tg * gen.hop / msg * 1e3,
+                          "gathered_bytes": int(yg.numel() * 2), "gathered_shape": list(yg.shape)}))
+
     # ---- config 4 / 5: clips -> HuBERT units (-> prosody -> vocoder)
     try:
         import torchaudio

@@ -42,9 +42,19 @@ def _worker(rank, world, port, ret):
         want0 = code.sum(1).float() + spkr.float()
         assert torch.equal(out[:, 0], want0)
         assert torch.equal(out[:, 1], torch.arange(world).repeat_interleave(B_local).float())
-        ret.put("ok")
     else:
         assert out is None
+    # int16 waveforms are gathered as raw bytes (NCCL has no 16-bit integer type) and come back as int16
+    w = (torch.arange(B_local * 6, dtype=torch.int32).reshape(B_local, 6) - 7 + 1000 * rank).to(torch.int16)
+    g16 = sb.gather(w)
+    if rank == 0:
+        assert g16.dtype == torch.int16 and g16.shape == (world * B_local, 6)
+        for r in range(world):
+            want = (torch.arange(B_local * 6, dtype=torch.int32).reshape(B_local, 6) - 7 + 1000 * r).to(torch.int16)
+            assert torch.equal(g16[r * B_local:(r + 1) * B_local], want)
+        ret.put("ok")
+    else:
+        assert g16 is None
     dist.barrier()
     dist.destroy_process_group()
 
