@@ -143,24 +143,27 @@ __global__ void __launch_bounds__(256) hub_conv0_apply_kernel(const float* wave,
 
 // ---- LayerNorm over channels, f32b in -> f32b and/or planes out ---------------------------------------------------
 // 8 lanes per row (frame); each lane keeps its 8-channel groups in registers (C <= 768 -> <= 12 groups per lane).
-template <int MAXG>
-__global__ void __launch_bounds__(256) hub_layernorm_kernel(const float* in, const float* gamma, const float* beta,
+// One CTA = 32 consecutive frames of one utterance x all channels: warp w owns the 8-channel groups w, w + 16, ...
+// and lane = frame, so every global access of a warp is 32 x 32 contiguous bytes; per-frame sums go through shared
+// memory (16 partials per frame).  G = C8 / 16 groups per thread (4 for 512 channels, 6 for 768).
+template <int G>
+__global__ void __launch_bounds__(512) hub_layernorm_kernel(const float* in, const float* gamma, const float* beta,
                                                             const int* lengths, int B, int C8, int T, int Tr, int Tp,
                                                             int halo, float* out_f, __half* out_hi, __half* out_lo) {
-  const int sub = threadIdx.x & 7;
-  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
-  const bool live = row < (long long)B * T;  // no early exit: the 8-lane shuffles below use the full-warp mask
-  if (!live) row = 0;
-  const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+  __shared__ float s_sum[16][32], s_sq[16][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (T + 31) / 32;
+  const int b = blockIdx.x / tiles, t = (blockIdx.x - b * tiles) * 32 + lane;
+  const bool live = t < T;
   const bool valid = live && t < (lengths ? min(T, lengths[b]) : T);
-  float x[MAXG][8];
+  float x[G][8];
   float s = 0.f;
 #pragma unroll
-  for (int g = 0; g < MAXG; ++g) {
-    const int c8 = sub + g * 8;
-    if (c8 < C8 && valid) {
-      const float* p = in + (((size_t)b * C8 + c8) * Tr + t) * 8;
-      const float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
+  for (int g = 0; g < G; ++g) {
+    const int c8 = warp + g * 16;
+    if (valid) {
+      float4 a, c;
+      ldg8(in + (((size_t)b * C8 + c8) * Tr + t) * 8, a, c);
       x[g][0] = a.x; x[g][1] = a.y; x[g][2] = a.z; x[g][3] = a.w;
       x[g][4] = c.x; x[g][5] = c.y; x[g][6] = c.z; x[g][7] = c.w;
     } else {
@@ -170,36 +173,39 @@ __global__ void __launch_bounds__(256) hub_layernorm_kernel(const float* in, con
 #pragma unroll
     for (int e = 0; e < 8; ++e) s += x[g][e];
   }
+  s_sum[warp][lane] = s;
+  __syncthreads();
+  s = 0.f;
 #pragma unroll
-  for (int o = 4; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int w = 0; w < 16; ++w) s += s_sum[w][lane];
   const float mean = s / (float)(C8 * 8);
   float q = 0.f;
 #pragma unroll
-  for (int g = 0; g < MAXG; ++g) {
-    if (sub + g * 8 < C8) {
+  for (int g = 0; g < G; ++g) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = x[g][e] - mean;
-        q = fmaf(d, d, q);
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float d = x[g][e] - mean;
+      q = fmaf(d, d, q);
     }
   }
+  s_sq[warp][lane] = q;
+  __syncthreads();
+  q = 0.f;
 #pragma unroll
-  for (int o = 4; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  for (int w = 0; w < 16; ++w) q += s_sq[w][lane];
   const float rstd = rsqrtf(q / (float)(C8 * 8) + 1e-5f);
+  if (!live) return;
 #pragma unroll
-  for (int g = 0; g < MAXG; ++g) {
-    const int c8 = sub + g * 8;
-    if (c8 >= C8 || !live) continue;
+  for (int g = 0; g < G; ++g) {
+    const int c8 = warp + g * 16;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8 + 4));
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float y[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      y[e] = valid ? fmaf((x[g][e] - mean) * rstd, __ldg(gamma + c8 * 8 + e), __ldg(beta + c8 * 8 + e)) : 0.f;
-    if (out_f) {
-      float* p = out_f + (((size_t)b * C8 + c8) * Tr + t) * 8;
-      *reinterpret_cast<float4*>(p) = make_float4(y[0], y[1], y[2], y[3]);
-      *reinterpret_cast<float4*>(p + 4) = make_float4(y[4], y[5], y[6], y[7]);
-    }
+    for (int e = 0; e < 8; ++e) y[e] = valid ? fmaf((x[g][e] - mean) * rstd, gm[e], bt[e]) : 0.f;
+    if (out_f) stg8(out_f + (((size_t)b * C8 + c8) * Tr + t) * 8, y);
     if (out_hi) {
       const size_t off = (((size_t)b * C8 + c8) * Tp + halo + t) * 8;
       split_store8(out_hi + off, out_lo + off, y);
@@ -338,65 +344,99 @@ __global__ void __launch_bounds__(128) hub_attention_kernel(const float* qkv, co
 
 // ---- k-means assignment ----------------------------------------------------------------------------------------------
 // one warp per frame; x f32b [B][D8][Tr][8]; centroids (K, D) row-major; units int64 (B, T) (-1 past the valid length)
+// A warp assigns kKmFrames consecutive frames at once: every centroid value it loads from L2 is used for all of them
+// (the one-frame-per-warp version pulled the whole 300 KB codebook through L2 for every frame: 0.32 ms per 32 clips).
+// The per-frame arithmetic and its order are unchanged -- 8 channels per lane and group, groups in order, xor-shuffle
+// tree, strict '<' so the first index wins ties -- so the units are bit-identical to the previous kernel's.
+constexpr int kKmFrames = 4;
 __global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, const float* cent, const int* lengths, int B,
                                                               int D8, int T, int Tr, int K, long long* units,
                                                               float* feat_out /* (B,T,D) or null */) {
-  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long w0 = ((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * kKmFrames;
   const int lane = threadIdx.x & 31;
-  if (wid >= (long long)B * T) return;
-  const int b = (int)(wid / T), t = (int)(wid - (long long)b * T);
-  const bool valid = t < (lengths ? min(T, lengths[b]) : T);
-  if (!valid) {
-    if (lane == 0) units[wid] = -1;
-    if (feat_out)
-      for (int i = lane; i < D8 * 8; i += 32) feat_out[wid * D8 * 8 + i] = 0.f;
-    return;
-  }
-  float v[4][8];  // D8 <= 128
+  const long long total = (long long)B * T;
+  if (w0 >= total) return;
+  float v[kKmFrames][4][8];  // D8 <= 128
+  bool valid[kKmFrames];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int c8 = lane + g * 32;
-    if (c8 < D8) {
-      const float* p = x + (((size_t)b * D8 + c8) * Tr + t) * 8;
-      const float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
-      v[g][0] = a.x; v[g][1] = a.y; v[g][2] = a.z; v[g][3] = a.w;
-      v[g][4] = c.x; v[g][5] = c.y; v[g][6] = c.z; v[g][7] = c.w;
-      if (feat_out) {
-        float* f = feat_out + wid * D8 * 8 + c8 * 8;
-        *reinterpret_cast<float4*>(f) = a;
-        *reinterpret_cast<float4*>(f + 4) = c;
+  for (int f = 0; f < kKmFrames; ++f) {
+    const long long wid = w0 + f;
+    valid[f] = false;
+    if (wid < total) {
+      const int b = (int)(wid / T), t = (int)(wid - (long long)b * T);
+      valid[f] = t < (lengths ? min(T, lengths[b]) : T);
+      if (!valid[f]) {
+        if (lane == 0) units[wid] = -1;
+        if (feat_out)
+          for (int i = lane; i < D8 * 8; i += 32) feat_out[wid * D8 * 8 + i] = 0.f;
       }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c8 = lane + g * 32;
+        float4 a = make_float4(0, 0, 0, 0), c = a;
+        if (valid[f] && c8 < D8) {
+          const float* p = x + (((size_t)b * D8 + c8) * Tr + t) * 8;
+          a = *reinterpret_cast<const float4*>(p);
+          c = *reinterpret_cast<const float4*>(p + 4);
+          if (feat_out) {
+            float* o = feat_out + wid * D8 * 8 + c8 * 8;
+            *reinterpret_cast<float4*>(o) = a;
+            *reinterpret_cast<float4*>(o + 4) = c;
+          }
+        }
+        v[f][g][0] = a.x; v[f][g][1] = a.y; v[f][g][2] = a.z; v[f][g][3] = a.w;
+        v[f][g][4] = c.x; v[f][g][5] = c.y; v[f][g][6] = c.z; v[f][g][7] = c.w;
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[f][g][e] = 0.f;
     }
   }
-  float best = INFINITY;
-  int besti = 0;
+  float best[kKmFrames];
+  int besti[kKmFrames];
+#pragma unroll
+  for (int f = 0; f < kKmFrames; ++f) { best[f] = INFINITY; besti[f] = 0; }
   for (int j = 0; j < K; ++j) {
-    float d = 0.f;
+    float d[kKmFrames];
+#pragma unroll
+    for (int f = 0; f < kKmFrames; ++f) d[f] = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const int c8 = lane + g * 32;
       if (c8 < D8) {
         const float* c = cent + (size_t)j * D8 * 8 + c8 * 8;
         const float4 a = __ldg(reinterpret_cast<const float4*>(c)), e = __ldg(reinterpret_cast<const float4*>(c + 4));
-        float u;
-        u = v[g][0] - a.x; d = fmaf(u, u, d);
-        u = v[g][1] - a.y; d = fmaf(u, u, d);
-        u = v[g][2] - a.z; d = fmaf(u, u, d);
-        u = v[g][3] - a.w; d = fmaf(u, u, d);
-        u = v[g][4] - e.x; d = fmaf(u, u, d);
-        u = v[g][5] - e.y; d = fmaf(u, u, d);
-        u = v[g][6] - e.z; d = fmaf(u, u, d);
-        u = v[g][7] - e.w; d = fmaf(u, u, d);
+#pragma unroll
+        for (int f = 0; f < kKmFrames; ++f) {
+          float u;
+          u = v[f][g][0] - a.x; d[f] = fmaf(u, u, d[f]);
+          u = v[f][g][1] - a.y; d[f] = fmaf(u, u, d[f]);
+          u = v[f][g][2] - a.z; d[f] = fmaf(u, u, d[f]);
+          u = v[f][g][3] - a.w; d[f] = fmaf(u, u, d[f]);
+          u = v[f][g][4] - e.x; d[f] = fmaf(u, u, d[f]);
+          u = v[f][g][5] - e.y; d[f] = fmaf(u, u, d[f]);
+          u = v[f][g][6] - e.z; d[f] = fmaf(u, u, d[f]);
+          u = v[f][g][7] - e.w; d[f] = fmaf(u, u, d[f]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (d < best) {  // strict: first index wins ties (argmin semantics)
-      best = d;
-      besti = j;
+    for (int f = 0; f < kKmFrames; ++f) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) d[f] += __shfl_xor_sync(0xffffffffu, d[f], o);
+      if (d[f] < best[f]) {  // strict: first index wins ties (argmin semantics)
+        best[f] = d[f];
+        besti[f] = j;
+      }
     }
   }
-  if (lane == 0) units[wid] = besti;
+  if (lane == 0) {
+#pragma unroll
+    for (int f = 0; f < kKmFrames; ++f)
+      if (valid[f]) units[w0 + f] = besti[f];
+  }
 }
 
 // standalone: x (M, D) row-major
@@ -570,12 +610,16 @@ static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
 
 static int hub_layernorm(const float* in, const float* gw, const float* gb, const int* lengths, int B, int C, int T, int Tr,
                          int Tp, float* out_f, __half* out_hi, __half* out_lo, cudaStream_t st) {
-  const long long threads = (long long)B * T * 8;
-  const int blocks = (int)((threads + 255) / 256);
-  if (C / 8 <= 64)
-    hub_layernorm_kernel<8><<<blocks, 256, 0, st>>>(in, gw, gb, lengths, B, C / 8, T, Tr, Tp, kHubHalo, out_f, out_hi, out_lo);
-  else
-    hub_layernorm_kernel<12><<<blocks, 256, 0, st>>>(in, gw, gb, lengths, B, C / 8, T, Tr, Tp, kHubHalo, out_f, out_hi, out_lo);
+  const int blocks = B * ((T + 31) / 32);
+#define HUB_LN(G) hub_layernorm_kernel<G><<<blocks, 512, 0, st>>>(in, gw, gb, lengths, B, C / 8, T, Tr, Tp, kHubHalo, out_f, out_hi, out_lo)
+  switch (C) {
+    case 256: HUB_LN(2); break;
+    case 512: HUB_LN(4); break;
+    case 768: HUB_LN(6); break;
+    case 1024: HUB_LN(8); break;
+    default: return set_err(DISSC_EUNSUPPORTED, "layer norm over %d channels (256 / 512 / 768 / 1024 supported)", C);
+  }
+#undef HUB_LN
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
@@ -845,7 +889,7 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     HUB_TRY(hub_layernorm(bf.Y, Ly.ln2_w, Ly.ln2_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
   }
   {
-    const long long threads = (long long)B * T * 32;
+    const long long threads = (((long long)B * T + kKmFrames - 1) / kKmFrames) * 32;
     hub_kmeans_f32b_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(bf.H, g->cent, lenT, B, D / 8, T, Tr, c.n_clusters,
                                                                          reinterpret_cast<long long*>(units), features);
     DISSC_CUDA(cudaGetLastError());
