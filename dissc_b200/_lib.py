@@ -45,7 +45,7 @@ EXPORTS = [
     "dissc_gen_create", "dissc_gen_destroy", "dissc_gen_hop", "dissc_gen_workspace_bytes", "dissc_gen_forward",
     "dissc_gen_forward_i16", "dissc_gen_forward_host", "dissc_gen_launches_per_forward", "dissc_gen_cost",
     "dissc_gen_profile", "dissc_conv1d_fused", "dissc_conv_transpose1d", "dissc_last_error", "dissc_version",
-    "dissc_gen_set_tensor_cores", "dissc_gen_tensor_core_stages", "dissc_conv1d_tc", "dissc_conv_transpose1d_tc", "dissc_tc_set_single_accumulator", "dissc_resblock_pair_tc",
+    "dissc_gen_set_tensor_cores", "dissc_gen_tensor_core_stages", "dissc_conv1d_tc", "dissc_conv_transpose1d_tc", "dissc_tc_set_single_accumulator", "dissc_tc_set_tuning", "dissc_resblock_pair_tc",
     "dissc_pred_create", "dissc_pred_destroy", "dissc_pred_workspace_bytes", "dissc_len_forward", "dissc_pitch_forward",
     "dissc_pitch_calc_freq", "dissc_len_carryover", "dissc_dedup_units", "dissc_repeat_interleave",
     "dissc_hubert_create", "dissc_hubert_destroy", "dissc_hubert_num_frames", "dissc_hubert_workspace_bytes",
@@ -87,6 +87,7 @@ def lib():
     L.dissc_gen_set_tensor_cores.argtypes = [c_void_p, c_int]
     L.dissc_gen_tensor_core_stages.argtypes = [c_void_p]
     L.dissc_tc_set_single_accumulator.argtypes = [c_int]
+    L.dissc_tc_set_tuning.argtypes = [c_int, c_int]
     L.dissc_conv1d_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                   c_float, c_float, c_void_p]

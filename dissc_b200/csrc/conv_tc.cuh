@@ -85,6 +85,7 @@ struct TcParams {
   int groups;            // grouped conv: chunk g reads channel blocks [g*n_cb, (g+1)*n_cb) and writes group_c8 8-channel
   int group_c8;          //   groups of output channels starting at g*group_c8 (NC >= 8*group_c8, padded columns dropped)
   int cout_log2;         // log2(Cout) when Cout is a power of two, else -1 (kTcUp needs it)
+  int split_w;           // EPW == 8 kernels: 1 = weights have their own producer thread (warp 2), 0 = warp 0 loads both
   int cb_split, k_hi;    // channel blocks >= cb_split carry only their first k_hi taps (the others are structural zeros:
                          //   the odd phase of a stride-2 conv in frame form); cb_split == 0: every block has k taps
 };
@@ -194,9 +195,18 @@ __device__ __forceinline__ void st_row8(float* p, const float v[8]) {
   }
 }
 
+// Warp roles: warp 0 = activation producer, warp 1 = MMA issuer + TMEM owner, [warp 2 = weight producer], then EPW epilogue
+// warps.  The one-CTA-per-SM variants (EPW == 8: the layers that STREAM their weights) give the weights their own producer
+// thread: a single in-order producer can only request the next activation block after it has queued all weight stages of
+// the current one, i.e. (ring depth) stages before the block is needed -- ncu showed the MMA thread re-trying 44 % of its
+// activation waits in the stage-1 k = 11 layers.  With two threads the block is requested the moment its buffer frees.
+__host__ __device__ constexpr int tc_pre_warps(int epw) { return epw == 8 ? 3 : 2; }
+__host__ __device__ constexpr int tc_threads(int epw) { return (tc_pre_warps(epw) + epw) * 32; }
+
 template <int NC, int EPW, int MODE>
-__global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 3 : 2)) conv_tc_kernel(const TcParams p) {
-  constexpr int kTcThreads = 64 + EPW * 32;
+__global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) ? 3 : 2)) conv_tc_kernel(const TcParams p) {
+  constexpr int PW = tc_pre_warps(EPW);   // warps in front of the epilogue warps
+  constexpr int kTcThreads = tc_threads(EPW);
   constexpr bool kTwoMma = (NC <= 128);
   constexpr bool kFast = (MODE != kTcGeneric);
   // switches the specialised modes fold away at compile time
@@ -270,8 +280,11 @@ __global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 
   pdl_wait();                 // the prologue above touched only weights / shared memory; activations from here on
   pdl_launch_dependents();
 
-  if (warp == 0) {
-    // ===================== producer: bulk TMA =====================
+  if (warp == 0 || (PW == 3 && warp == 2)) {
+    // ===================== producers: bulk TMA =====================
+    // PW == 2: warp 0 loads activation blocks AND weight stages (in MMA order).  PW == 3: warp 0 activations, warp 2 weights.
+    const bool split = (PW == 3) && p.split_w;
+    const bool do_a = (warp == 0), do_w = split ? (warp == 2) : (warp == 0);
     if (elect_one()) {
       uint32_t abuf = 0, aph = 0, ws = 0, wph = 0;
       bool first = true;
@@ -288,16 +301,18 @@ __global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 
         const unsigned char* wchunk = reinterpret_cast<const unsigned char*>(p.w) +
                                       (size_t)chunk * p.n_cb * p.k * w_tap_bytes;
         for (int cb = 0; cb < p.n_cb; ++cb) {
-          mbar_wait(&a_empty[abuf], aph ^ 1);
-          mbar_arrive_expect_tx(&a_full[abuf], a_bytes);
-          unsigned char* dst = sA + abuf * a_bytes;
-          for (int c8 = 0; c8 < kb8; ++c8) {
-            const size_t off = (size_t)(cb * kb8 + c8) * p.Tp_in * 8;
-            tma_load_1d(dst + (size_t)c8 * lbo_a, hi0 + off, lbo_a, &a_full[abuf]);
-            tma_load_1d(dst + a_plane_bytes + (size_t)c8 * lbo_a, lo0 + off, lbo_a, &a_full[abuf]);
+          if (do_a) {
+            mbar_wait(&a_empty[abuf], aph ^ 1);
+            mbar_arrive_expect_tx(&a_full[abuf], a_bytes);
+            unsigned char* dst = sA + abuf * a_bytes;
+            for (int c8 = 0; c8 < kb8; ++c8) {
+              const size_t off = (size_t)(cb * kb8 + c8) * p.Tp_in * 8;
+              tma_load_1d(dst + (size_t)c8 * lbo_a, hi0 + off, lbo_a, &a_full[abuf]);
+              tma_load_1d(dst + a_plane_bytes + (size_t)c8 * lbo_a, lo0 + off, lbo_a, &a_full[abuf]);
+            }
+            if (++abuf == (uint32_t)p.NA) { abuf = 0; aph ^= 1; }
           }
-          if (++abuf == (uint32_t)p.NA) { abuf = 0; aph ^= 1; }
-          if (!p.resident || first) {
+          if (do_w && (!p.resident || first)) {
             int j0 = 0;
             for (int g = 0; g < p.SPC; ++g, j0 += p.JG) {
               const int nt = min(p.JG, p.k - j0);
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(64 + EPW * 32, (EPW == 8) ? 1 : ((NC <= 32) ? 
     // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
     const int quarter = warp & 3;
     constexpr int NBH = NB / (EPW / 4);                 // epilogue batches per warp
-    const int bi0 = ((warp - 2) >> 2) * NBH;            // this warp's first batch (column half)
+    const int bi0 = ((warp - PW) >> 2) * NBH;           // this warp's first batch (column half)
     const int row = quarter * 32 + lane;
     const int cout8 = p.Cout / 8;
     uint32_t ab = 0, accph = 0;

@@ -167,6 +167,9 @@ static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
 // NC == 256: one accumulator (so TMEM double-buffers) instead of main+cross.  Measured end to end (profiles/README.md):
 // 1.8e-5 max-abs vs fp64 instead of 7e-6, stage 0 23 % faster.  DISSC_TC_SINGLE_ACC=0 restores the dual accumulator.
 static int g_single_acc256 = -1;
+// plan-time tuning knobs (dissc_tc_set_tuning): activation buffers preferred by the streamed-weight layers, and whether
+// the N >= 128 kernels use their separate weight-producer thread
+static int g_tc_na_pref = -1, g_tc_split_w = 1;
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
 bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc) {
@@ -221,11 +224,22 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
         }
       }
     }
-    const size_t fixed = 2 * a_bytes + misc(8);
-    if (budget > fixed + 2 * slot) {
-      L->resident = 0; L->NA = 2;
-      L->NS = (int)std::min<size_t>(8, (budget - fixed) / slot);
-      L->smem = 2 * a_bytes + (size_t)L->NS * slot + misc(L->NS);
+    // streamed weights.  The N >= 128 kernels have separate activation / weight producer threads, so a third activation
+    // buffer really doubles the prefetch window of a block (one loaded-HBM latency at N = 128, k = 11 with two); it is
+    // taken when >= 4 weight slots remain (the ring only has to cover the L2 latency).  DISSC_TC_NA=2 restores two.
+    if (g_tc_na_pref < 0) {
+      const char* e = getenv("DISSC_TC_NA");
+      g_tc_na_pref = e ? atoi(e) : 2;
+    }
+    L->split_w = g_tc_split_w;
+    for (int na = (NC >= 128) ? std::max(2, std::min(4, g_tc_na_pref)) : 2; na >= 2; --na) {
+      const size_t fixed = (size_t)na * a_bytes + misc(8);
+      if (budget <= fixed + 2 * slot) continue;
+      const int ns = (int)std::min<size_t>(8, (budget - fixed) / slot);
+      if (na > 2 && ns < 4) continue;
+      L->resident = 0; L->NA = na;
+      L->NS = ns;
+      L->smem = (size_t)na * a_bytes + (size_t)L->NS * slot + misc(L->NS);
       L->ctas_per_sm = ctas; L->ok = true;
       return true;
     }
@@ -291,7 +305,7 @@ static int launch_conv_tc_inst(const TcParams& p, const TcLayer& L, int grid, cu
                                     (int)(kSmemPerSm - 1024)));
     attr_set = true;
   }
-  DISSC_CUDA(launch_pdl(conv_tc_kernel<NC, EPW, MODE>, grid, 64 + EPW * 32, L.smem, st, p));
+  DISSC_CUDA(launch_pdl(conv_tc_kernel<NC, EPW, MODE>, grid, tc_threads(EPW), L.smem, st, p));
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
@@ -338,7 +352,7 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale;
   p.Cin8 = L.cin8_total ? L.cin8_total : L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
   p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
-  p.cb_split = L.cb_split; p.k_hi = L.k_hi;
+  p.cb_split = L.cb_split; p.k_hi = L.k_hi; p.split_w = L.split_w;
   p.cout_log2 = -1;
   for (int s = 3; s < 12; ++s)
     if ((1 << s) == L.Cout) p.cout_log2 = s;
@@ -1228,6 +1242,14 @@ int dissc_gen_set_tensor_cores(dissc_gen_t* g, int enable) {
   DISSC_CHECK(g, DISSC_EINVAL, "null handle");
   g->use_tc = enable != 0;
   return DISSC_OK;
+}
+
+int dissc_tc_set_tuning(int key, int value) {
+  switch (key) {
+    case 0: dissc::g_tc_na_pref = value; return DISSC_OK;
+    case 1: dissc::g_tc_split_w = value ? 1 : 0; return DISSC_OK;
+  }
+  return dissc::set_err(DISSC_EINVAL, "unknown tuning key %d", key);
 }
 
 int dissc_tc_set_single_accumulator(int enable) {

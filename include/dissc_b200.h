@@ -130,6 +130,10 @@ int dissc_gen_tensor_core_stages(const dissc_gen_t* g); /* how many stages curre
  * cross-term accumulators (7e-6).  Applies to handles / layer calls created afterwards.  Returns the previous setting
  * (-1 = never set: env DISSC_TC_SINGLE_ACC or the default decides). */
 int dissc_tc_set_single_accumulator(int enable);
+/* Plan-time tuning of the tensor-core conv kernel, read when a handle is created (A/B measurements, scripts/ab_tuning.py):
+ * key 0 = preferred number of activation buffers of the streamed-weight layers (2..4), key 1 = separate weight-producer
+ * thread in the N >= 128 kernels (0 / 1).  No reference counterpart. */
+int dissc_tc_set_tuning(int key, int value);
 
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
 int dissc_gen_launches_per_forward(const dissc_gen_t* g);
