@@ -165,3 +165,28 @@ def test_cuda_graph_replay_is_bit_identical(cuda_device):
     got = gi(code=code, f0=f0, spkr=spkr, lengths=lengths)
     torch.cuda.synchronize()
     assert got.dtype == torch.int16 and torch.equal(got, want)
+
+
+def test_tuning_knobs_do_not_change_results(cuda_device, vctk_gen):
+    """dissc_tc_set_tuning only moves work between producer threads / shared-memory buffers: every setting must give
+    the same bits (the arithmetic and its order are untouched)."""
+    from dissc_b200 import AttrDict, CodeGenerator, _lib
+    gen, sd = vctk_gen
+    code, f0, spkr = (t.to(cuda_device) for t in syn.synthetic_inputs(3, 40, seed=5))
+    want = gen(code=code, f0=f0, spkr=spkr)
+    L = _lib.lib()
+    try:
+        for split, na in ((0, 2), (1, 3), (0, 4)):
+            _lib.check(L.dissc_tc_set_tuning(1, split))
+            _lib.check(L.dissc_tc_set_tuning(0, na))
+            g = CodeGenerator(AttrDict(syn.VCTK_CONFIG)).to(cuda_device)
+            g.load_state_dict(sd)
+            g.eval()
+            g.remove_weight_norm()
+            got = g(code=code, f0=f0, spkr=spkr)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), (split, na)
+        assert L.dissc_tc_set_tuning(99, 0) != 0   # unknown key: error code, message in dissc_last_error()
+    finally:
+        L.dissc_tc_set_tuning(1, 1)
+        L.dissc_tc_set_tuning(0, 2)
