@@ -26,7 +26,6 @@
 #include "tc_host.cuh"
 #include "resblock_tc.cuh"
 #include "resblock64_tc.cuh"
-#include "resblock16_tc.cuh"
 
 namespace dissc {
 
@@ -391,7 +390,7 @@ int launch_zero_halos(__half* hi, __half* lo, int slabs, int Tp, int T, cudaStre
 // fused ResBlock pair (resblock_tc.cuh): plan + launch
 // ------------------------------------------------------------------------
 constexpr int kPairHalo = 32;    // f32h: slack rows in front of every slab (>= p1 + p2 = 30 for k=11, d=5)
-constexpr int kPairSlack = 352;  // f32h: Tpf = roundup(T,128) + kPairSlack (a 256-sample tile + k=11,d=5 halo reads 306 rows)
+constexpr int kPairSlack = 224;  // f32h: Tpf = roundup(T,128) + kPairSlack
 static int g_use_pair = -1;      // DISSC_TC_PAIR=0 disables the fused pair kernel
 
 struct PairLayer {
@@ -443,82 +442,6 @@ static int launch_pair(PairParams p, const PairLayer& L, const TcLayer& c1, cons
   const int grid = std::min(p.n_tiles, num_sms() * L.ctas_per_sm);
   if (L.C == 16) return launch_pair_nc<16>(p, L, grid, st);
   return launch_pair_nc<32>(p, L, grid, st);
-}
-
-// ------------------------------------------------------------------------
-// fused ResBlock pair, C = 16, conv2 in two-phase form (resblock16_tc.cuh)
-// ------------------------------------------------------------------------
-static int g_use_pair16 = -1;  // DISSC_TC_PAIR16=0: the C = 16 stage runs on resblock_tc.cuh like C = 32
-
-struct Pair16Layer {
-  bool ok = false;
-  int k = 0, dil = 1;
-  size_t smem = 0;
-  __half* v2 = nullptr;  // conv2 weights in two-phase form, device
-};
-
-static bool pair16_plan(int C, int k, int dil, const TcLayer& c1, const TcLayer& c2, Pair16Layer* L) {
-  L->ok = false;
-  if (g_use_pair16 < 0) {
-    const char* e = getenv("DISSC_TC_PAIR16");
-    g_use_pair16 = e ? (atoi(e) != 0) : 1;
-  }
-  // k = 3 pairs are bound by worker-warp instruction issue, not by the tensor pipe: they stay on resblock_tc.cuh (16 worker
-  // warps per SM instead of 12)
-  if (!g_use_pair16 || C != 16 || !(k & 1) || k < 7 || k > 33) return false;
-  if (!c1.ok || !c2.ok || c1.n_cb != 1 || c1.NC != 16 || c1.n_chunks != 1 || c1.KB != 16) return false;
-  const int p1 = dil * (k - 1) / 2, p2 = (k - 1) / 2;
-  if (p1 + p2 > kPairHalo || 256 - (k - 1) < 128) return false;
-  const size_t R1 = 256 + (size_t)(k - 1) * dil, R2 = 128 + (k + 1) / 2;
-  if (kPairHalo + R1 > (size_t)kPairSlack) return false;   // a tile's halo reads must stay inside its f32h slab
-  const size_t stg = 2 * R1 * 32, xop = 2 * 2 * R1 * 16, xt = 2 * 4 * R2 * 16, w1 = (size_t)k * 1024, v = (size_t)((k + 1) / 2) * 4096;
-  L->smem = kP16Groups * (stg + xop + xt) + w1 + v + 2 * 16 * 4 + (8 * kP16Groups + 1) * 8 + 128;
-  if (L->smem > kSmemPerSm - 1536) return false;
-  L->k = k; L->dil = dil; L->ok = true;
-  return true;
-}
-
-// conv2 weights (Cout, Cin, k), dilation 1, 'same' padding -> V[shift][chunk = (q', c8)][hi|lo][n = q*16 + co][8]:
-//   V_s[(q', ci), (q, co)] = W[co, ci, j = 2 s + q' - q]   (0 outside 0 <= j < k), scaled by 2^s like the plain packing
-static std::vector<__half> pack_v2_two_phase(const float* w, int k, float inv_scale) {
-  const int C = 16, NSH = (k + 1) / 2;
-  const float scale = 1.f / inv_scale;
-  std::vector<__half> out((size_t)NSH * 4 * 2 * 32 * 8);
-  size_t o = 0;
-  for (int s = 0; s < NSH; ++s)
-    for (int qp = 0; qp < 2; ++qp)
-      for (int c8 = 0; c8 < 2; ++c8) {
-        __half* hi = &out[o];
-        __half* lo = hi + 32 * 8;
-        o += 2 * 32 * 8;
-        for (int n = 0; n < 32; ++n)
-          for (int e = 0; e < 8; ++e) {
-            const int q = n / C, co = n % C, ci = c8 * 8 + e, j = 2 * s + qp - q;
-            const float v = (j >= 0 && j < k) ? w[((size_t)co * C + ci) * k + j] * scale : 0.f;
-            const __half h = __float2half_rn(v);
-            hi[n * 8 + e] = h;
-            lo[n * 8 + e] = __float2half_rn(v - __half2float(h));
-          }
-      }
-  return out;
-}
-
-static int launch_pair16(Pair16Params p, const Pair16Layer& L, const TcLayer& c1, const TcLayer& c2, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DISSC_CUDA(cudaFuncSetAttribute(resblock_pair16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(kSmemPerSm - 1024)));
-    attr_set = true;
-  }
-  p.k = L.k; p.dil = L.dil;
-  p.w1 = c1.w; p.v2 = L.v2; p.inv1 = c1.inv_scale; p.inv2 = c2.inv_scale;
-  const int m_out = 256 - (L.k - 1);
-  p.tiles_per_b = (p.T + m_out - 1) / m_out;
-  p.n_tiles = p.B * p.tiles_per_b;
-  const int grid = std::min(p.n_tiles, num_sms());
-  DISSC_CUDA(launch_pdl(resblock_pair16_tc_kernel, grid, kP16Threads, L.smem, st, p));
-  DISSC_CUDA(cudaGetLastError());
-  return DISSC_OK;
 }
 
 // ------------------------------------------------------------------------
@@ -620,8 +543,6 @@ struct dissc_gen {
   bool stage_tc[DISSC_MAX_STAGES] = {};
   PairLayer rb_pair[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // fused (c1,c2) pairs, narrow stages
   bool stage_pair[DISSC_MAX_STAGES] = {};
-  dissc::Pair16Layer rb_pair16[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // two-phase pairs of the C = 16 stage
-  bool stage_pair16[DISSC_MAX_STAGES] = {};
   dissc::Pair64Layer rb_pair64[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // fused pairs of the C = 64 stage
   bool stage_pair64[DISSC_MAX_STAGES] = {};
   TcLayer pre_tc, ups_tc[DISSC_MAX_STAGES];  // conv_pre / upsamplers on the tensor cores
@@ -970,17 +891,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
           }
           snprintf(name, sizeof(name), "s%d.rb%d.pair.%d.ptc", i, j, m);
           DISSC_TRY(L.begin(name, 2 * fl, by1 + by2));
-          if (g->stage_pair16[i] && g->rb_pair16[i][j][m].ok) {
-            Pair16Params q16{};
-            q16.x = q.x; q16.b1 = q.b1; q16.b2 = q.b2; q16.acc_in = q.acc_in; q16.out_f = q.out_f;
-            q16.out_hi = q.out_hi; q16.out_lo = q.out_lo; q16.out_plain = q.out_plain;
-            q16.lengths = q.lengths; q16.len_mul = q.len_mul;
-            q16.B = q.B; q16.T = q.T; q16.Tpf = q.Tpf; q16.f_halo = q.f_halo; q16.Tp = q.Tp; q16.p_halo = q.p_halo;
-            q16.div = q.div; q16.plain_act = q.plain_act; q16.plane_slope = q.plane_slope; q16.plain_slope = q.plain_slope;
-            DISSC_TRY(launch_pair16(q16, g->rb_pair16[i][j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], st));
-          } else {
-            DISSC_TRY(launch_pair(q, g->rb_pair[i][j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], st));
-          }
+          DISSC_TRY(launch_pair(q, g->rb_pair[i][j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], st));
           DISSC_TRY(L.end());
           continue;
         }
@@ -1280,16 +1191,6 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
       for (int m = 0; m < c.n_dil && g->stage_pair[i]; ++m)
         g->stage_pair[i] = pair_plan(c.c0 >> (i + 1), c.rk[j], c.dil[j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1],
                                      &g->rb_pair[i][j][m]);
-    // C = 16: the same pairs with conv2 in two-phase form (resblock16_tc.cuh); needs conv2's raw weights for the V packing
-    g->stage_pair16[i] = g->stage_pair[i] && (c.c0 >> (i + 1)) == 16;
-    for (int j = 0; j < c.n_rk && g->stage_pair16[i]; ++j)
-      for (int m = 0; m < c.n_dil; ++m) {
-        Pair16Layer* P = &g->rb_pair16[i][j][m];   // per layer: P->ok false -> resblock_tc.cuh runs this pair
-        if (!pair16_plan(16, c.rk[j], c.dil[j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], P)) continue;
-        const dissc_tensor* w2 = wm.get("resblocks." + std::to_string(i * c.n_rk + j) + ".convs2." + std::to_string(m) + ".weight");
-        if (!w2) { P->ok = false; continue; }
-        if ((rc = tc_upload(g, pack_v2_two_phase(w2->data, c.rk[j], g->rb_tc[i][j][m][1].inv_scale), &P->v2))) return fail(rc);
-      }
     // C = 64: planes-in / planes-out fused pairs with streamed weights (the stage after must not be the last one: its
     // output goes on as planes)
     g->stage_pair64[i] = g->tc_all && c.resblock == 1 && !g->stage_pair[i] && (c.c0 >> (i + 1)) == 64 && i + 1 < c.n_up;
@@ -1740,27 +1641,7 @@ int dissc_resblock_pair_tc(const float* in, const float* w1_host, const float* b
   p.lengths = lengths; p.len_mul = len_mul;
   p.B = B; p.T = T; p.Tpf = Tpf; p.f_halo = kPairHalo; p.Tp = Tp; p.p_halo = kTcHalo;
   p.div = div; p.plane_act = 1; p.plane_slope = plane_slope;
-  Pair16Layer L16;
-  if (!rc && pair16_plan(C, k, dilation, c1, c2, &L16)) {
-    // C = 16: the two-phase kernel (resblock16_tc.cuh) is what the model runs
-    auto v2 = pack_v2_two_phase(w2_host, k, c2.inv_scale);
-    __half* dv = (__half*)dalloc(v2.size() * 2);
-    if (!dv) {
-      cleanup();
-      return set_err(DISSC_ENOMEM, "cudaMalloc failed in dissc_resblock_pair_tc");
-    }
-    cudaMemcpyAsync(dv, v2.data(), v2.size() * 2, cudaMemcpyHostToDevice, st);
-    cudaStreamSynchronize(st);   // v2 is a host temporary
-    L16.v2 = dv;
-    Pair16Params q{};
-    q.x = p.x; q.b1 = p.b1; q.b2 = p.b2; q.acc_in = p.acc_in; q.out_f = p.out_f; q.out_hi = p.out_hi; q.out_lo = p.out_lo;
-    q.lengths = lengths; q.len_mul = len_mul;
-    q.B = B; q.T = T; q.Tpf = Tpf; q.f_halo = kPairHalo; q.Tp = Tp; q.p_halo = kTcHalo;
-    q.div = div; q.plane_slope = plane_slope;
-    rc = launch_pair16(q, L16, c1, c2, st);
-  } else if (!rc) {
-    rc = launch_pair(p, L, c1, c2, st);
-  }
+  if (!rc) rc = launch_pair(p, L, c1, c2, st);
   if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out + (size_t)kPairHalo * 8, out_raw, B, C, T, Tpf);
   if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp);
   cudaError_t e = cudaStreamSynchronize(st);
