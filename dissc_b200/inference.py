@@ -139,6 +139,32 @@ def write_wav(path: str, rate: int, audio: np.ndarray) -> None:
     write(path, rate, audio)
 
 
+class WavWriter:
+    """Peak-normalise + write wavs on a few background threads so the disk never stalls the next GPU batch (the reference
+    does both inline, once per utterance and target speaker: sr/inference.py:250-251).  ``close()`` waits for every file
+    and re-raises the first error."""
+
+    def __init__(self, workers: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        self._futs = []
+
+    @staticmethod
+    def _job(path, rate, audio, is_int16):
+        write_wav(path, rate, peak_normalize(audio) if is_int16 else peak_normalize_f32(audio))
+
+    def submit(self, path: str, rate: int, audio: np.ndarray) -> None:
+        self._futs.append(self._pool.submit(self._job, path, rate, audio, audio.dtype == np.int16))
+
+    def close(self) -> None:
+        try:
+            for f in self._futs:
+                f.result()
+        finally:
+            self._pool.shutdown(wait=True)
+            self._futs = []
+
+
 def batches_by_length(lengths: Sequence[int], max_batch: int, max_frames: int) -> List[List[int]]:
     """Greedy length-sorted batching: indices sorted by length (desc), cut when the padded batch would exceed
     ``max_batch`` rows or ``max_frames`` padded frames."""
@@ -365,10 +391,10 @@ def main(argv: Optional[Sequence[str]] = None):
             if "f0" in it:
                 it["f0"] = it["f0"][:n]
 
+    writer = WavWriter()
     if df is None and not a.unseen_speaker:                    # resynthesis (sr/inference.py:203-207)
         for i, audio in vocode_items(generator, my_items, device, None, a.batch).items():
-            write_wav(os.path.join(a.output_dir, out_name(my_items[i]) + "_gen.wav"), h.sampling_rate,
-                      peak_normalize(audio))
+            writer.submit(os.path.join(a.output_dir, out_name(my_items[i]) + "_gen.wav"), h.sampling_rate, audio)
     if h.get("multispkr", None) and a.vc:                      # voice conversion (sr/inference.py:209-251)
         if a.target_speakers is not None:
             spkrs = [spkr_to_id[s] for s in a.target_speakers]
@@ -397,13 +423,12 @@ def main(argv: Optional[Sequence[str]] = None):
                         my_items[j]["f0"] = rescale_f0(my_items[j]["f0"], *target_f0_stats(f0_tgt, k))
             sub = [my_items[j] for j in sel]
             for i, audio in vocode_items(generator, sub, device, k, a.batch).items():
-                write_wav(os.path.join(a.output_dir, out_name(sub[i]) + f"_{k}_gen.wav"), h.sampling_rate,
-                          peak_normalize(audio))
+                writer.submit(os.path.join(a.output_dir, out_name(sub[i]) + f"_{k}_gen.wav"), h.sampling_rate, audio)
     if write_gt:
         for it, gt in zip(my_items, gts):
             if gt is not None:
-                write_wav(os.path.join(a.output_dir, out_name(it) + "_gt.wav"), h.sampling_rate,
-                          peak_normalize_f32(gt))
+                writer.submit(os.path.join(a.output_dir, out_name(it) + "_gt.wav"), h.sampling_rate, gt)
+    writer.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -121,3 +121,24 @@ def test_code_file_sample_df_and_gt_audio(tmp_path):
     assert inf.load_gt_audio(tmp_path / "a.wav", 22050) is None          # other rate: skipped (resampy absent)
     assert inf.load_gt_audio(tmp_path / "missing.wav", 16000) is None
     assert np.allclose(inf.peak_normalize_f32(gt)[:4], x / 2000.0)
+
+
+def test_wav_writer_background_threads(tmp_path):
+    from scipy.io import wavfile
+    w = inf.WavWriter(workers=3)
+    want = {}
+    for i in range(7):
+        x = (np.arange(50, dtype=np.int32) * (i + 1) - 100).astype(np.int16)
+        w.submit(str(tmp_path / f"a{i}.wav"), 16000, x)
+        want[f"a{i}.wav"] = inf.peak_normalize(x)
+    g = np.linspace(-0.3, 0.6, 40).astype(np.float32)
+    w.submit(str(tmp_path / "gt.wav"), 16000, g)          # float input: normalised as a float signal
+    w.close()
+    for name, y in want.items():
+        rate, got = wavfile.read(tmp_path / name)
+        assert rate == 16000 and got.dtype == np.float32 and np.array_equal(got, y)
+    assert np.allclose(wavfile.read(tmp_path / "gt.wav")[1], g / 0.6)
+    bad = inf.WavWriter()
+    bad.submit(str(tmp_path / "no_such_dir" / "x.wav"), 16000, np.zeros(4, np.int16))
+    with pytest.raises(OSError):
+        bad.close()
