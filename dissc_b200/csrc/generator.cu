@@ -39,6 +39,15 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+// One-time per-(kernel, device) setup (cudaFuncSetAttribute is a per-device setting): slot of the current device in the
+// static flag arrays below.  Ordinals >= kMaxDevices share the last slot and simply repeat the (idempotent) call.
+constexpr int kMaxDevices = 64;
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < kMaxDevices - 1 ? dev : kMaxDevices - 1;
+}
+
 // ------------------------------------------------------------------------
 // weight packing (host)
 // ------------------------------------------------------------------------
@@ -74,10 +83,11 @@ template <int CO_TILE, int KW, int DIL, int CI_CHUNK, bool EMB>
 static int launch_conv_inst(const ConvParams& p, cudaStream_t st) {
   using C = ConvCfg<CO_TILE, KW, DIL, CI_CHUNK>;
   auto kern = conv1d_fused_kernel<CO_TILE, KW, DIL, CI_CHUNK, EMB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
+  const int dev_ = current_device_slot();
+  if (!attr_set[dev_]) {
     DISSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   dim3 grid((p.T + C::T_TILE - 1) / C::T_TILE, (p.Cout + CO_TILE - 1) / CO_TILE, p.B);
   kern<<<grid, kThreads, C::SMEM, st>>>(p);
@@ -124,10 +134,11 @@ template <int CO_TILE, int KW, int U>
 static int launch_convt_inst(const ConvTParams& p, cudaStream_t st) {
   using C = ConvTCfg<CO_TILE, KW, U, 8>;
   auto kern = convt1d_kernel<CO_TILE, KW, U, 8>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
+  const int dev_ = current_device_slot();
+  if (!attr_set[dev_]) {
     DISSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   const int n_frames = (p.Tout + p.pad - 1) / U + 1;
   dim3 grid((n_frames + C::F_TILE - 1) / C::F_TILE, (p.Cout + CO_TILE - 1) / CO_TILE, p.B);
@@ -299,11 +310,12 @@ static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem,
 
 template <int NC, int EPW, int MODE>
 static int launch_conv_tc_inst(const TcParams& p, const TcLayer& L, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
+  const int dev_ = current_device_slot();
+  if (!attr_set[dev_]) {
     DISSC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NC, EPW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(kSmemPerSm - 1024)));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   DISSC_CUDA(launch_pdl(conv_tc_kernel<NC, EPW, MODE>, grid, tc_threads(EPW), L.smem, st, p));
   DISSC_CUDA(cudaGetLastError());
@@ -422,11 +434,12 @@ static bool pair_plan(int C, int k, int dil, const TcLayer& c1, const TcLayer& c
 
 template <int NC>
 static int launch_pair_nc(const PairParams& p, const PairLayer& L, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
+  const int dev_ = current_device_slot();
+  if (!attr_set[dev_]) {
     DISSC_CUDA(cudaFuncSetAttribute(resblock_pair_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(kSmemPerSm - 1024)));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   DISSC_CUDA(launch_pdl(resblock_pair_tc_kernel<NC>, grid, PairCfg<NC>::THREADS, L.smem, st, p));
   DISSC_CUDA(cudaGetLastError());
@@ -482,11 +495,12 @@ static bool pair64_plan(int C, int k, int dil, const TcLayer& c1, const TcLayer&
 }
 
 static int launch_pair64(Pair64Params p, const Pair64Layer& L, const TcLayer& c1, const TcLayer& c2, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
+  const int dev_ = current_device_slot();
+  if (!attr_set[dev_]) {
     DISSC_CUDA(cudaFuncSetAttribute(resblock_pair64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(kSmemPerSm - 1024)));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   p.k = L.k; p.dil = L.dil; p.NS = L.NS;
   p.w1 = c1.w; p.w2 = c2.w; p.inv1 = c1.inv_scale; p.inv2 = c2.inv_scale;

@@ -797,11 +797,8 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     const int Tp = (int)ru(Tq, 128) + 2 * kHubHalo;
     HUB_TRY(launch_zero_halos(bf.dA[0], bf.dA[1], B * 2 * C / 8, Tp, Tq, st, kHubHalo));
     const size_t smem = (size_t)(kConv0Chunk * kConv0S + kConv0K + 2 + C * kConv0K) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-      DISSC_CUDA(cudaFuncSetAttribute(hub_conv0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
+    // per-device setting, a few microseconds: set on every call rather than caching a per-process flag
+    DISSC_CUDA(cudaFuncSetAttribute(hub_conv0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     // chunks cover every frame up to the rounded-up row count so that rows >= T0 inside [0, Tq) are written as zeros
     const int nchunk_apply = (2 * Tq + kConv0Chunk - 1) / kConv0Chunk;
     hub_conv0_apply_kernel<<<dim3(nchunk_apply, B), 256, smem, st>>>(wave, g->w0, bf.gn_ss, bf.lens, N, C, Tp, kHubHalo,
