@@ -49,7 +49,8 @@ EXPORTS = [
     "dissc_pred_create", "dissc_pred_destroy", "dissc_pred_workspace_bytes", "dissc_len_forward", "dissc_pitch_forward",
     "dissc_pitch_calc_freq", "dissc_len_carryover", "dissc_dedup_units", "dissc_repeat_interleave",
     "dissc_hubert_create", "dissc_hubert_destroy", "dissc_hubert_num_frames", "dissc_hubert_workspace_bytes",
-    "dissc_hubert_forward", "dissc_kmeans_assign",
+    "dissc_hubert_forward", "dissc_kmeans_assign", "dissc_gen_status", "dissc_pred_status",
+    "dissc_gen_forward_host_submit", "dissc_gen_forward_host_wait", "dissc_gen_host_reserve",
 ]
 
 
@@ -103,8 +104,14 @@ def lib():
                                     c_void_p, c_size_t, c_void_p]
     L.dissc_pitch_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p]
-    L.dissc_pitch_calc_freq.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+    L.dissc_pitch_calc_freq.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p]
+    L.dissc_gen_forward_host_submit.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                                c_void_p, c_void_p]
+    L.dissc_gen_forward_host_wait.argtypes = [c_void_p, c_int]
+    L.dissc_gen_host_reserve.argtypes = [c_void_p, c_int, c_int]
+    L.dissc_gen_status.argtypes = [c_void_p]
+    L.dissc_pred_status.argtypes = [c_void_p]
     L.dissc_len_carryover.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.dissc_dedup_units.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.dissc_repeat_interleave.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
@@ -121,7 +128,12 @@ def lib():
     return L
 
 
+EINDEX = -6
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().dissc_last_error().decode("utf-8", "replace")
+        if rc == EINDEX:   # what nn.Embedding raises for an id outside its table
+            raise IndexError(f"{what or 'dissc_b200 call'}: {msg}")
         raise DisscError(f"{what or 'dissc_b200 call'} failed ({rc}): {msg}")

@@ -99,6 +99,19 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Embedding-row ids come from the caller (unit ids from a k-means model, speaker ids from a manifest): nn.Embedding
+// raises on an id outside the table (device assert on CUDA); here the gather stays inside the table (row 0 is read
+// instead) and the handle's error flag -- an int in mapped pinned host memory -- is set, which the next host-synchronous
+// entry point (dissc_*_status, dissc_gen_forward_host) turns into DISSC_EINDEX.
+enum { kIdxUnit = 1, kIdxSpeaker = 2 };
+__device__ __forceinline__ long long checked_row(long long id, int rows, int* err_flag, int what) {
+  if ((unsigned long long)id >= (unsigned long long)rows) {
+    if (err_flag) atomicOr_system(err_flag, what);
+    return 0;
+  }
+  return id;
+}
+
 // leaky-relu for 0 <= slope <= 1 (the reference uses 0.1 and 0.01): max(v, v*slope) is two instructions, bit-identical
 // to the select form for every finite v.
 __device__ __forceinline__ float leaky(float v, float slope) { return fmaxf(v, v * slope); }

@@ -32,6 +32,8 @@ struct ConvParams {
   const float* dict_w;    // (num_embeddings, E)
   const float* spkr_w;    // (rows, E)
   int E, f0_ch, spk_base; // f0_ch = -1 if absent; spk_base = first speaker channel or -1
+  int n_code_rows, n_spkr_rows;  // table rows: ids outside [0, rows) set *err (common.cuh::checked_row)
+  int* err;
 
   const float* w;       // packed [co_tile][chunk][CI_CHUNK][KW][CO_TILE], zero padded
   const float* bias;    // (Cout)
@@ -106,11 +108,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_fused_kernel(const ConvPar
         if (ci < p.Cin && t >= 0 && t < Tvalid) {
           if constexpr (IN_EMBED) {
             if (ci < p.E) {
-              v = __ldg(p.dict_w + (size_t)p.code[(size_t)b * p.T + t] * p.E + ci);
+              v = __ldg(p.dict_w + (size_t)checked_row(p.code[(size_t)b * p.T + t], p.n_code_rows, p.err, kIdxUnit) * p.E + ci);
             } else if (ci == p.f0_ch) {
               v = __ldg(p.f0 + (size_t)b * p.T + t);
             } else {
-              v = __ldg(p.spkr_w + (size_t)p.spkr[b] * p.E + (ci - p.spk_base));
+              v = __ldg(p.spkr_w + (size_t)checked_row(p.spkr[b], p.n_spkr_rows, p.err, kIdxSpeaker) * p.E + (ci - p.spk_base));
             }
           } else {
             v = __ldg(p.in + ((size_t)b * p.Cin + ci) * p.T + t);

@@ -88,6 +88,11 @@ struct TcParams {
   int split_w;           // EPW == 8 kernels: 1 = weights have their own producer thread (warp 2), 0 = warp 0 loads both
   int cb_split, k_hi;    // channel blocks >= cb_split carry only their first k_hi taps (the others are structural zeros:
                          //   the odd phase of a stride-2 conv in frame form); cb_split == 0: every block has k taps
+  // Activation scale (powers of two, chosen per tensor at load time so the fp16 hi / lo planes sit in the middle of the
+  // fp16 range whatever the magnitude of the activations; exact in fp32, so results do not depend on it unless a plane
+  // would otherwise underflow / saturate).  The INPUT planes hold value * in_scale: the host folds 1 / in_scale into
+  // w_inv_scale.  The OUTPUT planes are written as act(value) * plane_scale.  0 means 1.
+  float in_scale, plane_scale;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
   const float* const res_p = (MODE == kTcUp) ? nullptr : p.res;
   const float* const acc_p = (MODE == kTcUp) ? nullptr : p.acc_in;
   const float div = p.div;  // unused by kTcUp
+  const float plane_scale = p.plane_scale;
   const int single_acc = (NC == 256) ? p.single_acc : 0;
   constexpr int G = NC / 8;            // 8-channel groups per chunk
   constexpr int EB = 2;                // groups per epilogue batch
@@ -516,7 +522,8 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
             if (valid) {
               float a[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] = kFast ? leaky(v[i], p.plane_slope) : tc_act(v[i], p.plane_act, p.plane_slope);
+              for (int i = 0; i < 8; ++i)
+                a[i] = (kFast ? leaky(v[i], p.plane_slope) : tc_act(v[i], p.plane_act, p.plane_slope)) * plane_scale;
               split_store8(p.out_hi + pidx, p.out_lo + pidx, a);
             } else {
               *reinterpret_cast<uint4*>(p.out_hi + pidx) = make_uint4(0, 0, 0, 0);
@@ -575,6 +582,9 @@ struct EmbedParams {
   const int* lengths;
   int E, f0_ch, spk_base, Cin;  // f0_ch / spk_base = -1 if absent
   int B, C8, T, Tp;
+  float scale;                   // planes hold value * scale (TcParams::in_scale of conv_pre)
+  int n_code_rows, n_spkr_rows;  // table rows: ids outside [0, rows) set *err (common.cuh::checked_row)
+  int* err;
   __half* hi;
   __half* lo;
 };
@@ -593,14 +603,14 @@ static __global__ void tc_embed_planes_kernel(const EmbedParams p) {
       float x = 0.f;
       if (t >= 0 && t < Tvalid && ci < p.Cin) {
         if (ci < p.E) {
-          x = __ldg(p.dict_w + (size_t)p.code[(size_t)b * p.T + t] * p.E + ci);
+          x = __ldg(p.dict_w + (size_t)checked_row(p.code[(size_t)b * p.T + t], p.n_code_rows, p.err, kIdxUnit) * p.E + ci);
         } else if (ci == p.f0_ch) {
           x = __ldg(p.f0 + (size_t)b * p.T + t);
         } else if (p.spk_base >= 0 && ci >= p.spk_base) {
-          x = __ldg(p.spkr_w + (size_t)p.spkr[b] * p.E + (ci - p.spk_base));
+          x = __ldg(p.spkr_w + (size_t)checked_row(p.spkr[b], p.n_spkr_rows, p.err, kIdxSpeaker) * p.E + (ci - p.spk_base));
         }
       }
-      v[e] = x;
+      v[e] = x * p.scale;
     }
     split_store8(p.hi + (size_t)i * 8, p.lo + (size_t)i * 8, v);
   }
@@ -609,7 +619,7 @@ static __global__ void tc_embed_planes_kernel(const EmbedParams p) {
 // plain (B,C,T) fp32 -> split planes [B][C8][Tp][8] (+ optional leaky-relu); rows >= valid length and channels >= C
 // are zero.  Layer-test helper (the model writes planes straight from the producing kernel's epilogue).
 static __global__ void tc_pack_planes_kernel(const float* in, __half* hi, __half* lo, const int* lengths, int len_mul, int B, int C,
-                                      int C8, int T, int Tp, int act, float slope) {
+                                      int C8, int T, int Tp, int act, float slope, float scale = 1.f) {
   const long long total = (long long)B * C8 * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % T);
@@ -621,7 +631,7 @@ static __global__ void tc_pack_planes_kernel(const float* in, __half* hi, __half
     for (int e = 0; e < 8; ++e) {
       const int c = c8 * 8 + e;
       float x = (t < Tvalid && c < C) ? in[((size_t)b * C + c) * T + t] : 0.f;
-      v[e] = act ? leaky(x, slope) : x;
+      v[e] = (act ? leaky(x, slope) : x) * scale;
     }
     const size_t off = ((size_t)s * Tp + kTcHalo + t) * 8;
     split_store8(hi + off, lo + off, v);
@@ -648,14 +658,15 @@ static __global__ void tc_f32b_to_plain_kernel(const float* in, float* out, int 
   }
 }
 // planes -> plain fp32 (hi + lo), for tests
-static __global__ void tc_planes_to_plain_kernel(const __half* hi, const __half* lo, float* out, int B, int C, int T, int Tp) {
+static __global__ void tc_planes_to_plain_kernel(const __half* hi, const __half* lo, float* out, int B, int C, int T, int Tp,
+                                                 float unscale = 1.f) {
   const long long total = (long long)B * C * T;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % T);
     const long long bc = i / T;
     const int c = (int)(bc % C), b = (int)(bc / C);
     const size_t off = (((size_t)b * (C / 8) + c / 8) * Tp + kTcHalo + t) * 8 + (c & 7);
-    out[i] = __half2float(hi[off]) + __half2float(lo[off]);
+    out[i] = (__half2float(hi[off]) + __half2float(lo[off])) * unscale;
   }
 }
 

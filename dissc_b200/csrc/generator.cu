@@ -39,6 +39,25 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+int err_flag_create(ErrFlag* f) {
+  DISSC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&f->host), 64, cudaHostAllocMapped));
+  *f->host = 0;
+  DISSC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&f->dev), f->host, 0));
+  return DISSC_OK;
+}
+void err_flag_destroy(ErrFlag* f) {
+  if (f->host) cudaFreeHost(f->host);
+  f->host = f->dev = nullptr;
+}
+int err_flag_take(ErrFlag* f, const char* what, int unit_rows, int spkr_rows) {
+  if (!f->host) return DISSC_OK;
+  const int v = __atomic_exchange_n(f->host, 0, __ATOMIC_ACQ_REL);
+  if (!v) return DISSC_OK;
+  return set_err(DISSC_EINDEX, "%s: index out of range in self:%s%s%s (unit table has %d rows, speaker table %d)", what,
+                 (v & kIdxUnit) ? " unit id" : "", (v & kIdxUnit) && (v & kIdxSpeaker) ? " and" : "",
+                 (v & kIdxSpeaker) ? " speaker id" : "", unit_rows, spkr_rows);
+}
+
 // One-time per-(kernel, device) setup (cudaFuncSetAttribute is a per-device setting): slot of the current device in the
 // static flag arrays below.  Ordinals >= kMaxDevices share the last slot and simply repeat the (idempotent) call.
 constexpr int kMaxDevices = 64;
@@ -275,15 +294,19 @@ static bool tc_plan_convt(int Cin, int Cout, int k, int u, TcLayer* L) {
   return true;
 }
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device (one cached value per device ordinal; relaxed atomics: racing threads compute the
+// same number).
 static int num_sms() {
-  if (g_num_sms == 0) {
+  static int cache[kMaxDevices] = {};
+  const int slot = current_device_slot();
+  int n = __atomic_load_n(&cache[slot], __ATOMIC_RELAXED);
+  if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    __atomic_store_n(&cache[slot], n, __ATOMIC_RELAXED);
   }
-  return g_num_sms;
+  return n;
 }
 
 // Launch with the programmatic-stream-serialization attribute (PDL, common.cuh): only for kernels that call pdl_wait()
@@ -361,7 +384,9 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   if (L.groups) { p.groups = 1; p.group_c8 = L.group_c8; }
   p.k = L.k; p.dil = L.dil; p.pad = L.pad; p.KB = L.KB; p.n_cb = L.n_cb; p.JG = L.JG; p.SPC = L.SPC; p.NS = L.NS;
   p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.acc_cols = L.acc_cols; p.nbuf = L.nbuf; p.NA = L.NA;
-  p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale;
+  if (p.in_scale == 0.f) p.in_scale = 1.f;
+  if (p.plane_scale == 0.f) p.plane_scale = 1.f;
+  p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale / p.in_scale;   // powers of two: exact
   p.Cin8 = L.cin8_total ? L.cin8_total : L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
   p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
   p.cb_split = L.cb_split; p.k_hi = L.k_hi; p.split_w = L.split_w;
@@ -448,7 +473,10 @@ static int launch_pair_nc(const PairParams& p, const PairLayer& L, int grid, cud
 
 static int launch_pair(PairParams p, const PairLayer& L, const TcLayer& c1, const TcLayer& c2, cudaStream_t st) {
   p.k = L.k; p.dil = L.dil; p.tmem_cols = L.tmem_cols;
-  p.w1 = c1.w; p.w2 = c2.w; p.inv1 = c1.inv_scale; p.inv2 = c2.inv_scale;
+  if (p.in_scale == 0.f) p.in_scale = 1.f;
+  if (p.xt_scale == 0.f) p.xt_scale = 1.f;
+  if (p.plane_scale == 0.f) p.plane_scale = 1.f;
+  p.w1 = c1.w; p.w2 = c2.w; p.inv1 = c1.inv_scale / p.in_scale; p.inv2 = c2.inv_scale / p.xt_scale;
   const int m_out = 128 - (L.k - 1);
   p.tiles_per_b = (p.T + m_out - 1) / m_out;
   p.n_tiles = p.B * p.tiles_per_b;
@@ -503,7 +531,10 @@ static int launch_pair64(Pair64Params p, const Pair64Layer& L, const TcLayer& c1
     attr_set[dev_] = true;
   }
   p.k = L.k; p.dil = L.dil; p.NS = L.NS;
-  p.w1 = c1.w; p.w2 = c2.w; p.inv1 = c1.inv_scale; p.inv2 = c2.inv_scale;
+  if (p.in_scale == 0.f) p.in_scale = 1.f;
+  if (p.xt_scale == 0.f) p.xt_scale = 1.f;
+  if (p.plane_scale == 0.f) p.plane_scale = 1.f;
+  p.w1 = c1.w; p.w2 = c2.w; p.inv1 = c1.inv_scale / p.in_scale; p.inv2 = c2.inv_scale / p.xt_scale;
   if (p.halo == 0) p.halo = kTcHalo;
   const int m_out = 128 - (L.k - 1);
   p.tiles_per_b = (p.T + m_out - 1) / m_out;
@@ -565,11 +596,20 @@ struct dissc_gen {
   float* dict_w = nullptr;
   float* spkr_w = nullptr;
   int n_launches = 0;
+  dissc::ErrFlag err;  // out-of-range unit / speaker ids (dissc_gen_status)
+  // power-of-two activation scales of the split-fp16 planes (estimate_act_scales): embedding planes, conv_pre output,
+  // per stage the residual stream x (x_up and every r) and the stage output, per conv pair the intermediate xt
+  float s_emb = 1.f, s_pre = 1.f, s_x[DISSC_MAX_STAGES], s_out[DISSC_MAX_STAGES];
+  float s_xt[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];
   // host-entry staging arena
   void* arena = nullptr;
   size_t arena_bytes = 0;
-  cudaStream_t hstream = nullptr;
+  cudaStream_t hstream = nullptr;                  // compute stream of the host entry points
+  cudaStream_t cstream = nullptr;                  // copy-back stream
+  cudaEvent_t fwd_done[2] = {nullptr, nullptr};    // per slot: forward finished (compute stream)
+  cudaEvent_t d2h_done[2] = {nullptr, nullptr};    // per slot: output is in host memory (copy stream)
 };
+constexpr int kHostSlots = 2;
 
 namespace dissc {
 
@@ -657,6 +697,87 @@ static int make_convt(dissc_gen* g, const WeightMap& wm, const std::string& pref
   return dev_upload(g, b->data, Cout, &L->bias);
 }
 
+// ------------------------------------------------------------------------
+// Activation scale of the split-fp16 planes
+// ------------------------------------------------------------------------
+// A plane pair represents x as fp16 hi + fp16 lo.  That is fp32-accurate while |x| sits well inside the fp16 range:
+// `lo` keeps all 11 bits for |x| >= 2^-3 and `hi` saturates at 65504.  The weights get their own power-of-two scale
+// (pack_weights_tc); the activations get one per tensor, estimated HERE from the weights alone: a second-moment
+// propagation through the graph (mean square of every tensor under independent zero-mean inputs: a conv multiplies it
+// by sum(w^2) / Cout and adds mean(b^2); leaky-relu(0.1) keeps 0.505 of it; a residual add sums; the MRF mean keeps it),
+// and each plane is scaled so its estimated RMS lands in [16, 32): values from RMS / 128 to RMS * 2047 are exact to 22
+// bits.  The estimate only has to be right within a few octaves; being powers of two the scales change no result bit
+// unless a plane would otherwise leave that window (tests/test_layers_gpu.py::*_activation_scale_sweep,
+// tests/test_generator_gpu.py::test_config2_rows_vs_oracle on the N(0, 0.01) `init_weights` recipe, whose late
+// activations are ~1e-5).  DISSC_ACT_SCALE=0 forces every scale to 1.
+static float pow2_scale_for_rms(double rms) {
+  if (!(rms > 0.0) || !std::isfinite(rms)) return 1.f;
+  int e = 0;
+  std::frexp(rms, &e);   // rms = f * 2^e, f in [0.5, 1)
+  const int sh = std::max(-40, std::min(40, 5 - e));
+  return std::ldexp(1.f, sh);
+}
+static double mean_sq(const dissc_tensor* t) {
+  if (!t || t->numel <= 0) return 0.0;
+  double a = 0.0;
+  for (int64_t i = 0; i < t->numel; ++i) a += (double)t->data[i] * t->data[i];
+  return a / (double)t->numel;
+}
+// second-moment gain of a conv: sum(w^2) / n_out_positions_per_weight_set, plus mean(b^2)
+static void conv_moments(const WeightMap& wm, const std::string& prefix, int Cout, int stride, double* gain, double* b2) {
+  const dissc_tensor* w = wm.get(prefix + ".weight");
+  const dissc_tensor* b = wm.get(prefix + ".bias");
+  *gain = w ? mean_sq(w) * (double)w->numel / ((double)Cout * stride) : 0.0;
+  *b2 = mean_sq(b);
+}
+static void estimate_act_scales(dissc_gen* g, const WeightMap& wm) {
+  const dissc_gen_cfg& c = g->cfg;
+  g->s_emb = g->s_pre = 1.f;
+  for (int i = 0; i < DISSC_MAX_STAGES; ++i) {
+    g->s_x[i] = g->s_out[i] = 1.f;
+    for (int j = 0; j < DISSC_MAX_KERNELS; ++j)
+      for (int m = 0; m < DISSC_MAX_DILATIONS; ++m) g->s_xt[i][j][m] = 1.f;
+  }
+  if (const char* e = getenv("DISSC_ACT_SCALE"))
+    if (atoi(e) == 0) return;
+  if (!g->tc_all) return;   // mixed pipelines (a CUDA-core upsampler writing planes) keep unscaled planes
+  constexpr double kLrelu = 0.505;   // E[lrelu(x, 0.1)^2] / E[x^2] for a symmetric x
+  const double ms_dict = mean_sq(wm.get("dict.weight")), ms_spk = c.has_spkr ? mean_sq(wm.get("spkr.weight")) : 0.0;
+  const double ms_f0 = c.has_f0 ? 1.0 : 0.0;   // speaker-normalised F0, sr/dataset.py:297-312
+  g->s_emb = pow2_scale_for_rms(std::sqrt(std::max(ms_dict, std::max(ms_spk, ms_f0))));
+  double ms = (c.embedding_dim * ms_dict + ms_f0 + (c.has_spkr ? c.embedding_dim * ms_spk : 0.0)) / std::max(1, c.model_in_dim);
+  double gain, b2;
+  conv_moments(wm, "conv_pre", c.c0, 1, &gain, &b2);
+  ms = ms * gain + b2;
+  g->s_pre = pow2_scale_for_rms(std::sqrt(kLrelu * ms));
+  for (int i = 0; i < c.n_up; ++i) {
+    const int ch = c.c0 >> (i + 1);
+    conv_moments(wm, "ups." + std::to_string(i), ch, c.up_rates[i], &gain, &b2);
+    const double ms_up = kLrelu * ms * gain + b2;
+    g->s_x[i] = pow2_scale_for_rms(std::sqrt(kLrelu * ms_up));
+    double ms_sum = 0.0;
+    for (int j = 0; j < c.n_rk; ++j) {
+      const std::string p = "resblocks." + std::to_string(i * c.n_rk + j);
+      double ms_r = ms_up;
+      for (int m = 0; m < c.n_dil; ++m) {
+        if (c.resblock == 1) {
+          conv_moments(wm, p + ".convs1." + std::to_string(m), ch, 1, &gain, &b2);
+          const double ms_xt = kLrelu * ms_r * gain + b2;
+          g->s_xt[i][j][m] = pow2_scale_for_rms(std::sqrt(kLrelu * ms_xt));
+          conv_moments(wm, p + ".convs2." + std::to_string(m), ch, 1, &gain, &b2);
+          ms_r += kLrelu * ms_xt * gain + b2;
+        } else {
+          conv_moments(wm, p + ".convs." + std::to_string(m), ch, 1, &gain, &b2);
+          ms_r += kLrelu * ms_r * gain + b2;
+        }
+      }
+      ms_sum += ms_r;
+    }
+    ms = ms_sum / std::max(1, c.n_rk);
+    g->s_out[i] = pow2_scale_for_rms(std::sqrt(kLrelu * ms));
+  }
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -733,6 +854,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
   int dev = -1;
   DISSC_CUDA(cudaGetDevice(&dev));
   DISSC_CHECK(dev == g->device, DISSC_EINVAL, "current device %d != handle device %d", dev, g->device);
+  DISSC_TRY(err_flag_take(&g->err, "an earlier forward", g->cfg.num_embeddings, g->cfg.n_spkr_rows));
 
   const size_t RS = region_bytes(g, B, T);
   char* wsb = static_cast<char*>(workspace);
@@ -767,7 +889,8 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     e.E = c.embedding_dim; e.f0_ch = c.has_f0 ? c.embedding_dim : -1;
     e.spk_base = c.has_spkr ? c.embedding_dim + (c.has_f0 ? 1 : 0) : -1;
     e.Cin = c.model_in_dim; e.B = B; e.C8 = g->pre_tc.Cin_pad / 8; e.T = T; e.Tp = Tp0;
-    e.hi = P_emb.hi; e.lo = P_emb.lo;
+    e.hi = P_emb.hi; e.lo = P_emb.lo; e.scale = g->s_emb;
+    e.n_code_rows = c.num_embeddings; e.n_spkr_rows = c.n_spkr_rows; e.err = g->err.dev;
     DISSC_TRY(L.begin("embed", 0));
     const long long tot = (long long)B * e.C8 * Tp0;
     tc_embed_planes_kernel<<<(int)std::min<long long>((tot + 255) / 256, 148 * 8), 256, 0, st>>>(e);
@@ -779,6 +902,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     TcParams p{};
     p.a_hi = P_emb.hi; p.a_lo = P_emb.lo; p.bias = g->pre.bias;
     p.out_hi = P_act[0].hi; p.out_lo = P_act[0].lo; p.plane_act = 1; p.plane_slope = 0.1f;
+    p.in_scale = g->s_emb; p.plane_scale = g->s_pre;
     p.lengths = lengths; p.len_mul = 1;
     p.B = B; p.T = T; p.Tr = Tr0; p.Tp = Tp0; p.Tp_in = Tp0;
     DISSC_TRY(L.begin("conv_pre.tc", 2.0 * g->pre.Cin * g->pre.Cout * g->pre.k * (double)T * B,
@@ -796,6 +920,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     p.E = c.embedding_dim;
     p.f0_ch = c.has_f0 ? c.embedding_dim : -1;
     p.spk_base = c.has_spkr ? c.embedding_dim + (c.has_f0 ? 1 : 0) : -1;
+    p.n_code_rows = c.num_embeddings; p.n_spkr_rows = c.n_spkr_rows; p.err = g->err.dev;
     p.w = g->pre.w; p.bias = g->pre.bias; p.out = act[0];
     p.lengths = lengths; p.len_mul = 1;
     p.B = B; p.Cin = g->pre.Cin; p.Cout = g->pre.Cout; p.T = T; p.pad = g->pre.pad;
@@ -847,6 +972,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
       TcParams p{};
       p.a_hi = P_act[cur].hi; p.a_lo = P_act[cur].lo; p.bias = U.bias;
       p.out_f32b = F_up; p.out_hi = P_up.hi; p.out_lo = P_up.lo; p.plane_act = 1; p.plane_slope = 0.1f;
+      p.in_scale = (i == 0) ? g->s_pre : g->s_out[i - 1]; p.plane_scale = g->s_x[i];
       p.lengths = lengths; p.len_mul = mul * U.u;
       p.B = B; p.T = Tout; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp_in;
       if (pair) {  // the fused pairs read x as fp32 only
@@ -888,6 +1014,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
           q.b1 = c1.bias; q.b2 = g->rb[i][j][m][1].bias;
           q.lengths = lengths; q.len_mul = mul;
           q.B = B; q.T = Tcur; q.Tpf = Tpf; q.f_halo = kPairHalo; q.Tp = Tp; q.p_halo = kTcHalo;
+          q.in_scale = g->s_x[i]; q.xt_scale = g->s_xt[i][j][m]; q.plane_scale = g->s_out[i];
           if (!last_m) {
             q.out_f = F_rr[m & 1];
           } else {
@@ -919,6 +1046,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
           q.lengths = lengths; q.len_mul = mul;
           q.B = B; q.T = Tcur; q.Tp = Tp; q.Tr = Tr; q.halo = kTcHalo;
           q.plane_slope = 0.1f;
+          q.in_scale = g->s_x[i]; q.xt_scale = g->s_xt[i][j][m]; q.plane_scale = g->s_x[i];
           if (!last_m) {
             q.out_hi = PP[m & 1].hi; q.out_lo = PP[m & 1].lo;
           } else {
@@ -928,6 +1056,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
             } else {
               q.div = (float)c.n_rk;
               q.out_hi = P_act[cur ^ 1].hi; q.out_lo = P_act[cur ^ 1].lo; q.plane_slope = next_slope;
+              q.plane_scale = g->s_out[i];
             }
           }
           snprintf(name, sizeof(name), "s%d.rb%d.pair.%d.p64", i, j, m);
@@ -947,6 +1076,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
             TcParams p = base;
             p.a_hi = rin_p.hi; p.a_lo = rin_p.lo; p.bias = c1.bias;
             p.out_hi = P_xt.hi; p.out_lo = P_xt.lo; p.plane_act = 1; p.plane_slope = 0.1f;
+            p.in_scale = g->s_x[i]; p.plane_scale = g->s_xt[i][j][m];
             snprintf(name, sizeof(name), "s%d.rb%d.c1.%d.tc", i, j, m);
             DISSC_TRY(L.begin(name, fl, by1));
             DISSC_TRY(launch_conv_tc(p, g->rb_tc[i][j][m][0], Tcur, st));
@@ -957,8 +1087,10 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
           TcParams q = base;
           const Planes qin = (c.resblock == 1) ? P_xt : rin_p;
           q.a_hi = qin.hi; q.a_lo = qin.lo; q.bias = g->rb[i][j][m][which].bias; q.res = rin_f;
+          q.in_scale = (c.resblock == 1) ? g->s_xt[i][j][m] : g->s_x[i];
           if (!last_m) {
             q.out_f32b = F_r; q.out_hi = P_r.hi; q.out_lo = P_r.lo; q.plane_act = 1; q.plane_slope = 0.1f;
+            q.plane_scale = g->s_x[i];
           } else {
             if (j > 0) q.acc_in = F_xs;
             if (!last_j) {
@@ -967,6 +1099,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
               q.div = (float)c.n_rk;
               if (tc_all && !last_stage) {
                 q.out_hi = P_act[cur ^ 1].hi; q.out_lo = P_act[cur ^ 1].lo; q.plane_act = 1; q.plane_slope = next_slope;
+                q.plane_scale = g->s_out[i];
               } else {
                 q.out_plain = xs; q.plain_act = 1; q.plain_slope = next_slope;
               }
@@ -1036,6 +1169,36 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
   return DISSC_OK;
 }
 
+// Layer-test helpers: the test entry points pick the activation scales from the tensors they are handed (absmax -> a
+// power of two), which a model does at load time from its weights (estimate_act_scales).  Synchronous; test entries only.
+static double device_absmax(const float* d, size_t n, cudaStream_t st) {
+  if (!d || !n) return 0.0;
+  std::vector<float> h(n);
+  cudaStreamSynchronize(st);
+  if (cudaMemcpy(h.data(), d, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
+  double m = 0.0;
+  for (float v : h)
+    if (std::isfinite(v)) m = std::max(m, (double)std::fabs(v));
+  return m;
+}
+static double host_absmax(const float* h, size_t n) {
+  double m = 0.0;
+  for (size_t i = 0; h && i < n; ++i) m = std::max(m, (double)std::fabs(h[i]));
+  return m;
+}
+// largest l2 norm of one output channel's weights: the typical |output| of a conv is this times the input's RMS
+static double host_row_norm(const float* w, int rows, size_t per_row) {
+  double m = 0.0;
+  for (int r = 0; w && r < rows; ++r) {
+    double a = 0.0;
+    for (size_t i = 0; i < per_row; ++i) a += (double)w[r * per_row + i] * w[r * per_row + i];
+    m = std::max(m, std::sqrt(a));
+  }
+  return m;
+}
+// scale that puts `absmax` at ~2^9 (the RMS of a Gaussian-ish tensor then sits near 2^7; 2^7 headroom to 65504)
+static float pow2_scale_for_absmax(double absmax) { return pow2_scale_for_rms(absmax / 32.0); }
+
 // Layer-level test of the C = 64 fused pair: plain (B,64,T) fp32 in, raw x' [+acc][/div] and leaky-relu planes out.
 static int pair64_layer_test(const float* in, const float* w1_host, const float* b1_host, const float* w2_host,
                              const float* b2_host, const float* acc_in, float* out_raw, float* out_planes,
@@ -1086,13 +1249,18 @@ static int pair64_layer_test(const float* in, const float* w1_host, const float*
   cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
   cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
   const int nb = 148 * 4;
-  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, i_hi, i_lo, lengths, len_mul, B, C, C / 8, T, Tp, 1, 0.1f);
+  const double ax = device_absmax(in, (size_t)B * C * T, st), aacc = device_absmax(acc_in, acc_in ? (size_t)B * C * T : 0, st);
+  const double axt = ax * host_row_norm(w1_host, C, (size_t)C * k) + host_absmax(b1_host, C);
+  const double aout = ax + axt * host_row_norm(w2_host, C, (size_t)C * k) + host_absmax(b2_host, C) + aacc;
+  const float s_in = pow2_scale_for_absmax(ax), s_xt = pow2_scale_for_absmax(axt), s_out = pow2_scale_for_absmax(aout);
+  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, i_hi, i_lo, lengths, len_mul, B, C, C / 8, T, Tp, 1, 0.1f, s_in);
   int rc = launch_zero_halos(i_hi, i_lo, B * C / 8, Tp, T, st);
   if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * C / 8, Tp, T, st);
   if (acc_in) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(acc_in, f_acc, B, C, T, Tr);
   c1.w = dw1; c2.w = dw2;
   Pair64Params p{};
   p.x_hi = i_hi; p.x_lo = i_lo; p.in_inv_slope = 10.0f;
+  p.in_scale = s_in; p.xt_scale = s_xt; p.plane_scale = s_out;
   p.b1 = db; p.b2 = db + C; p.acc_in = acc_in ? f_acc : nullptr;
   p.out_f = f_out; p.out_hi = out_planes ? o_hi : nullptr; p.out_lo = out_planes ? o_lo : nullptr;
   p.lengths = lengths; p.len_mul = len_mul;
@@ -1100,7 +1268,7 @@ static int pair64_layer_test(const float* in, const float* w1_host, const float*
   p.div = div; p.plane_slope = plane_slope;
   if (!rc) rc = launch_pair64(p, L, c1, c2, st);
   if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, C, T, Tr);
-  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp, 1.f / s_out);
   cudaError_t e = cudaStreamSynchronize(st);
   cleanup();
   if (rc) return rc;
@@ -1133,6 +1301,11 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
               "model_in_dim=%d but embedding_dim/f0/multispkr give %d channels (extra conditioning features such as "
               "f0_stats are not supported)",
               c.model_in_dim, expect_in);
+  struct DeviceGuard {   // the caller's current device is restored on every exit path
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  cudaGetDevice(&guard.prev);
   DISSC_CUDA(cudaSetDevice(device));
   WeightMap wm;
   for (int i = 0; i < n_weights; ++i) wm.m[weights[i].name] = &weights[i];
@@ -1145,6 +1318,7 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
     return rc;
   };
   int rc;
+  if ((rc = err_flag_create(&g->err))) return fail(rc);
   if ((rc = make_conv(g, wm, "conv_pre", c.model_in_dim, c.c0, 7, 1, &g->pre))) return fail(rc);
   int ch = c.c0;
   g->hop = 1;
@@ -1237,20 +1411,35 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
   }
   g->n_launches = 1 + c.n_up * (1 + c.n_rk * c.n_dil * (c.resblock == 1 ? 2 : 1)) + 1;
   if (const char* e = getenv("DISSC_TC")) g->use_tc = atoi(e) != 0;
+  estimate_act_scales(g, wm);
   *out = g;
   return DISSC_OK;
 }
 
 void dissc_gen_destroy(dissc_gen_t* g) {
   if (!g) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(g->device);
   for (void* p : g->allocs) cudaFree(p);
   if (g->arena) cudaFree(g->arena);
   if (g->hstream) cudaStreamDestroy(g->hstream);
+  if (g->cstream) cudaStreamDestroy(g->cstream);
+  for (int i = 0; i < kHostSlots; ++i) {
+    if (g->fwd_done[i]) cudaEventDestroy(g->fwd_done[i]);
+    if (g->d2h_done[i]) cudaEventDestroy(g->d2h_done[i]);
+  }
+  err_flag_destroy(&g->err);
   delete g;
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 int dissc_gen_hop(const dissc_gen_t* g) { return g ? g->hop : 0; }
+
+int dissc_gen_status(dissc_gen_t* g) {
+  DISSC_CHECK(g, DISSC_EINVAL, "null handle");
+  return err_flag_take(&g->err, "CodeGenerator forward", g->cfg.num_embeddings, g->cfg.n_spkr_rows);
+}
 
 int dissc_gen_set_tensor_cores(dissc_gen_t* g, int enable) {
   DISSC_CHECK(g, DISSC_EINVAL, "null handle");
@@ -1300,35 +1489,82 @@ int dissc_gen_forward_i16(dissc_gen_t* g, const int64_t* code, const float* f0, 
                       static_cast<cudaStream_t>(stream), nullptr);
 }
 
-int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
-                           const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16) {
+// ---- host entry points -----------------------------------------------------------------------------------------
+// Two input / output slots in device memory, one compute stream, one copy-back stream:
+//   compute stream : H2D(slot s) -> forward(slot s)                 (one shared workspace: forwards are stream-ordered)
+//   copy stream    : wait(forward s done) -> D2H(slot s) -> d2h_done[s]
+// so with two batches in flight the 12-25 MB D2H of batch i rides under the forward of batch i+1.
+static int host_arena_reserve(dissc_gen* g, int B, int T) {
+  size_t ws = 0;
+  dissc_gen_workspace_bytes(g, B, T, &ws);
+  const size_t n_out = (size_t)B * out_len(g, T);
+  const size_t b_io = align_up((size_t)B * T * 8, 256) + align_up((size_t)B * T * 4, 256) + align_up((size_t)B * 8, 256) +
+                      align_up((size_t)B * 4, 256) + align_up(n_out * 4, 256);
+  const size_t total = kHostSlots * b_io + ws;
+  if (total <= g->arena_bytes) return DISSC_OK;
+  // growing the arena: nothing may still be using the old one
+  if (g->hstream) DISSC_CUDA(cudaStreamSynchronize(g->hstream));
+  if (g->cstream) DISSC_CUDA(cudaStreamSynchronize(g->cstream));
+  if (g->arena) DISSC_CUDA(cudaFree(g->arena));
+  g->arena = nullptr;
+  g->arena_bytes = 0;
+  DISSC_CUDA(cudaMalloc(&g->arena, total));
+  g->arena_bytes = total;
+  return DISSC_OK;
+}
+
+static int host_streams(dissc_gen* g) {
+  if (!g->hstream) DISSC_CUDA(cudaStreamCreateWithFlags(&g->hstream, cudaStreamNonBlocking));
+  if (!g->cstream) DISSC_CUDA(cudaStreamCreateWithFlags(&g->cstream, cudaStreamNonBlocking));
+  for (int i = 0; i < kHostSlots; ++i) {
+    if (!g->fwd_done[i]) DISSC_CUDA(cudaEventCreateWithFlags(&g->fwd_done[i], cudaEventDisableTiming));
+    if (!g->d2h_done[i]) DISSC_CUDA(cudaEventCreateWithFlags(&g->d2h_done[i], cudaEventDisableTiming));
+  }
+  return DISSC_OK;
+}
+
+int dissc_gen_host_reserve(dissc_gen_t* g, int B, int T) {
+  DISSC_CHECK(g && B > 0 && T > 0, DISSC_EINVAL, "bad argument");
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  cudaGetDevice(&guard.prev);
+  DISSC_CUDA(cudaSetDevice(g->device));
+  DISSC_TRY(host_streams(g));
+  return host_arena_reserve(g, B, T);
+}
+
+int dissc_gen_forward_host_submit(dissc_gen_t* g, int slot, const int64_t* code, const float* f0, const int64_t* spkr,
+                                  const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16) {
   DISSC_CHECK(g && code && ((out_f32 != nullptr) != (out_i16 != nullptr)), DISSC_EINVAL,
               "need a handle, code and exactly one output buffer");
+  DISSC_CHECK(slot >= 0 && slot < kHostSlots, DISSC_EINVAL, "slot %d outside [0, %d)", slot, kHostSlots);
   DISSC_CHECK(B > 0 && T > 0, DISSC_EINVAL, "B=%d T=%d must be positive", B, T);
+  struct DeviceGuard {   // the caller's current device is restored on every exit path
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  cudaGetDevice(&guard.prev);
   DISSC_CUDA(cudaSetDevice(g->device));
-  if (!g->hstream) DISSC_CUDA(cudaStreamCreateWithFlags(&g->hstream, cudaStreamNonBlocking));
+  DISSC_TRY(host_streams(g));
+  DISSC_TRY(host_arena_reserve(g, B, T));
   size_t ws = 0;
   dissc_gen_workspace_bytes(g, B, T, &ws);
   const size_t n_out = (size_t)B * out_len(g, T);
   const size_t b_code = align_up((size_t)B * T * 8, 256), b_f0 = align_up((size_t)B * T * 4, 256),
-               b_spk = align_up((size_t)B * 8, 256), b_len = align_up((size_t)B * 4, 256),
-               b_out = align_up(n_out * (out_f32 ? 4 : 2), 256);
-  const size_t total = b_code + b_f0 + b_spk + b_len + b_out + ws;
-  if (total > g->arena_bytes) {
-    if (g->arena) DISSC_CUDA(cudaFree(g->arena));
-    g->arena = nullptr;
-    g->arena_bytes = 0;
-    DISSC_CUDA(cudaMalloc(&g->arena, total));
-    g->arena_bytes = total;
-  }
-  char* a = static_cast<char*>(g->arena);
+               b_spk = align_up((size_t)B * 8, 256), b_len = align_up((size_t)B * 4, 256), b_out = align_up(n_out * 4, 256);
+  const size_t b_io = b_code + b_f0 + b_spk + b_len + b_out;
+  char* a = static_cast<char*>(g->arena) + (size_t)slot * b_io;
   int64_t* d_code = reinterpret_cast<int64_t*>(a);
   float* d_f0 = reinterpret_cast<float*>(a + b_code);
   int64_t* d_spk = reinterpret_cast<int64_t*>(a + b_code + b_f0);
   int32_t* d_len = reinterpret_cast<int32_t*>(a + b_code + b_f0 + b_spk);
   char* d_out = a + b_code + b_f0 + b_spk + b_len;
-  void* d_ws = d_out + b_out;
+  void* d_ws = static_cast<char*>(g->arena) + (size_t)kHostSlots * b_io;
   cudaStream_t st = g->hstream;
+  // the slot's previous copy-back must have left its output buffer before this forward overwrites it
+  DISSC_CUDA(cudaStreamWaitEvent(st, g->d2h_done[slot], 0));
   DISSC_CUDA(cudaMemcpyAsync(d_code, code, (size_t)B * T * 8, cudaMemcpyHostToDevice, st));
   if (f0) DISSC_CUDA(cudaMemcpyAsync(d_f0, f0, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
   if (spkr) DISSC_CUDA(cudaMemcpyAsync(d_spk, spkr, (size_t)B * 8, cudaMemcpyHostToDevice, st));
@@ -1337,12 +1573,29 @@ int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0,
                         out_f32 ? reinterpret_cast<float*>(d_out) : nullptr,
                         out_i16 ? reinterpret_cast<int16_t*>(d_out) : nullptr, d_ws, ws, st, nullptr);
   if (rc) return rc;
+  DISSC_CUDA(cudaEventRecord(g->fwd_done[slot], st));
+  DISSC_CUDA(cudaStreamWaitEvent(g->cstream, g->fwd_done[slot], 0));
   if (out_f32)
-    DISSC_CUDA(cudaMemcpyAsync(out_f32, d_out, n_out * 4, cudaMemcpyDeviceToHost, st));
+    DISSC_CUDA(cudaMemcpyAsync(out_f32, d_out, n_out * 4, cudaMemcpyDeviceToHost, g->cstream));
   else
-    DISSC_CUDA(cudaMemcpyAsync(out_i16, d_out, n_out * 2, cudaMemcpyDeviceToHost, st));
-  DISSC_CUDA(cudaStreamSynchronize(st));
+    DISSC_CUDA(cudaMemcpyAsync(out_i16, d_out, n_out * 2, cudaMemcpyDeviceToHost, g->cstream));
+  DISSC_CUDA(cudaEventRecord(g->d2h_done[slot], g->cstream));
   return DISSC_OK;
+}
+
+int dissc_gen_forward_host_wait(dissc_gen_t* g, int slot) {
+  DISSC_CHECK(g, DISSC_EINVAL, "null handle");
+  DISSC_CHECK(slot >= 0 && slot < kHostSlots, DISSC_EINVAL, "slot %d outside [0, %d)", slot, kHostSlots);
+  if (!g->d2h_done[slot]) return DISSC_OK;   // nothing was ever submitted
+  DISSC_CUDA(cudaEventSynchronize(g->d2h_done[slot]));
+  return err_flag_take(&g->err, "CodeGenerator forward", g->cfg.num_embeddings, g->cfg.n_spkr_rows);
+}
+
+int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
+                           const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16) {
+  int rc = dissc_gen_forward_host_submit(g, 0, code, f0, spkr, lengths, B, T, out_f32, out_i16);
+  if (rc) return rc;
+  return dissc_gen_forward_host_wait(g, 0);
 }
 
 int dissc_gen_cost(const dissc_gen_t* g, int B, int T, double* flops, double* bytes) {
@@ -1498,7 +1751,12 @@ int dissc_conv1d_tc(const float* in, const float* w_host, const float* bias_host
   cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
   cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
   const int nb = 148 * 4;
-  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, Cin, cin8, T, Tp, pre_act, pre_slope);
+  const double ax = device_absmax(in, (size_t)B * Cin * T, st);
+  const double aout = ax * host_row_norm(w_host, Cout, (size_t)Cin * k) + host_absmax(bias_host, Cout) +
+                      device_absmax(res, res ? (size_t)B * Cout * T : 0, st) +
+                      device_absmax(acc_in, acc_in ? (size_t)B * Cout * T : 0, st);
+  const float s_in = pow2_scale_for_absmax(ax), s_out = pow2_scale_for_absmax(aout);
+  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, Cin, cin8, T, Tp, pre_act, pre_slope, s_in);
   int rc = launch_zero_halos(a_hi, a_lo, B * cin8, Tp, T, st);
   if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * Cout / 8, Tp, T, st);
   if (res) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(res, f_res, B, Cout, T, Tr);
@@ -1513,9 +1771,10 @@ int dissc_conv1d_tc(const float* in, const float* w_host, const float* bias_host
   p.lengths = lengths; p.len_mul = len_mul;
   p.B = B; p.T = T; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp;
   p.div = div; p.plane_act = post_act; p.plane_slope = post_slope; p.plain_act = post_act; p.plain_slope = post_slope;
+  p.in_scale = s_in; p.plane_scale = s_out;
   if (!rc) rc = launch_conv_tc(p, L, T, st);
   if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, Cout, T, Tr);
-  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, Cout, T, Tp);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, Cout, T, Tp, 1.f / s_out);
   cudaError_t e = cudaStreamSynchronize(st);
   cleanup();
   if (rc) return rc;
@@ -1573,7 +1832,13 @@ int dissc_conv_transpose1d_tc(const float* in, const float* w_host, const float*
   cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
   cudaMemsetAsync(f_out, 0x7b, f_elems * 4, st);
   const int nb = 148 * 4;
-  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, Cin, cin8, T_in, Tp_in, 0, 0.f);
+  const double ax = device_absmax(in, (size_t)B * Cin * T_in, st);
+  // (Cin, Cout, k): bound the output by the input's absmax times the largest l2 norm over a whole input-channel row set
+  const double aout = ax * std::sqrt((double)host_row_norm(w_host, 1, (size_t)Cin * Cout * k) *
+                                     host_row_norm(w_host, 1, (size_t)Cin * Cout * k) / std::max(1, Cout * u)) +
+                      host_absmax(bias_host, Cout);
+  const float s_in = pow2_scale_for_absmax(ax), s_out = pow2_scale_for_absmax(aout);
+  tc_pack_planes_kernel<<<nb, 256, 0, st>>>(in, a_hi, a_lo, lengths, len_mul, B, Cin, cin8, T_in, Tp_in, 0, 0.f, s_in);
   int rc = launch_zero_halos(a_hi, a_lo, B * cin8, Tp_in, T_in, st);
   if (!rc) rc = launch_zero_halos(o_hi, o_lo, B * Cout / 8, Tp, Tout, st);
   L.w = dw;
@@ -1582,10 +1847,11 @@ int dissc_conv_transpose1d_tc(const float* in, const float* w_host, const float*
   p.out_f32b = f_out; p.out_hi = o_hi; p.out_lo = o_lo; p.plane_act = 1; p.plane_slope = plane_slope;
   p.lengths = lengths; p.len_mul = len_mul * u;
   p.B = B; p.T = Tout; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp_in;
+  p.in_scale = s_in; p.plane_scale = s_out;
   const int n_frames = (Tout + pad - 1) / u + 1;
   if (!rc) rc = launch_conv_tc(p, L, n_frames, st);
   if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out, out_raw, B, Cout, Tout, Tr);
-  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, Cout, Tout, Tp);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, Cout, Tout, Tp, 1.f / s_out);
   cudaError_t e = cudaStreamSynchronize(st);
   cleanup();
   if (rc) return rc;
@@ -1645,6 +1911,10 @@ int dissc_resblock_pair_tc(const float* in, const float* w1_host, const float* b
   cudaMemsetAsync(o_hi, 0x7b, plane_elems * 2, st);
   cudaMemsetAsync(o_lo, 0x7b, plane_elems * 2, st);
   const int nb = 148 * 4;
+  const double ax = device_absmax(in, (size_t)B * C * T, st), aacc = device_absmax(acc_in, acc_in ? (size_t)B * C * T : 0, st);
+  const double axt = ax * host_row_norm(w1_host, C, (size_t)C * k) + host_absmax(b1_host, C);
+  const double aout = ax + axt * host_row_norm(w2_host, C, (size_t)C * k) + host_absmax(b2_host, C) + aacc;
+  const float s_in = pow2_scale_for_absmax(ax), s_xt = pow2_scale_for_absmax(axt), s_out = pow2_scale_for_absmax(aout);
   tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(in, f_in + (size_t)kPairHalo * 8, B, C, T, Tpf);
   if (acc_in) tc_plain_to_f32b_kernel<<<nb, 256, 0, st>>>(acc_in, f_acc + (size_t)kPairHalo * 8, B, C, T, Tpf);
   int rc = launch_zero_halos(o_hi, o_lo, B * C / 8, Tp, T, st);
@@ -1655,9 +1925,10 @@ int dissc_resblock_pair_tc(const float* in, const float* w1_host, const float* b
   p.lengths = lengths; p.len_mul = len_mul;
   p.B = B; p.T = T; p.Tpf = Tpf; p.f_halo = kPairHalo; p.Tp = Tp; p.p_halo = kTcHalo;
   p.div = div; p.plane_act = 1; p.plane_slope = plane_slope;
+  p.in_scale = s_in; p.xt_scale = s_xt; p.plane_scale = s_out;
   if (!rc) rc = launch_pair(p, L, c1, c2, st);
   if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out + (size_t)kPairHalo * 8, out_raw, B, C, T, Tpf);
-  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp);
+  if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp, 1.f / s_out);
   cudaError_t e = cudaStreamSynchronize(st);
   cleanup();
   if (rc) return rc;

@@ -28,7 +28,8 @@ struct PredConv {
 
 // token_emb[seq] ++ (spk_emb[spk] [+ pe[t]])  ->  (B, 2E, L) fp32, zero at t >= lengths[b]
 __global__ void pred_embed_kernel(const long long* seq, const long long* spk, const int* lengths, const float* tok_w,
-                                  const float* spk_w, const float* pe, int E, int B, int L, float* out) {
+                                  const float* spk_w, const float* pe, int E, int B, int L, float* out, int tok_rows,
+                                  int spk_rows, int* err) {
   const long long total = (long long)B * 2 * E * L;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % L);
@@ -38,9 +39,9 @@ __global__ void pred_embed_kernel(const long long* seq, const long long* spk, co
     float v = 0.f;
     if (t < n) {
       if (c < E) {
-        v = __ldg(tok_w + (size_t)seq[(size_t)b * L + t] * E + c);
+        v = __ldg(tok_w + (size_t)checked_row(seq[(size_t)b * L + t], tok_rows, err, kIdxUnit) * E + c);
       } else {
-        v = __ldg(spk_w + (size_t)spk[b] * E + (c - E));
+        v = __ldg(spk_w + (size_t)checked_row(spk[b], spk_rows, err, kIdxSpeaker) * E + (c - E));
         if (pe) v = v + __ldg(pe + (size_t)t * E + (c - E));  // PositionalEncoding.forward, :31-38
       }
     }
@@ -60,14 +61,19 @@ __global__ void pred_affine_kernel(const float* x, float scale, float shift, con
 
 // calc_freq (model/pitch_predictor.py:100-104): (class > 0) * (norm ? reg : mean[spk] + reg * std[spk])
 __global__ void pitch_calc_freq_kernel(const float* cls, const float* reg, const long long* spk, const float* mean,
-                                       const float* stdv, const int* lengths, int B, int L, float* out) {
+                                       const float* stdv, int n_rows, const int* lengths, int B, int L, float* out) {
   const int total = B * L;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int b = i / L, t = i - b * L;
     const int n = lengths ? min(L, lengths[b]) : L;
     float r = reg[i];
-    if (mean) r = __fadd_rn(mean[spk[b]], __fmul_rn(r, stdv[spk[b]]));
-    out[i] = (t < n && cls[i] > 0.f) ? r : 0.f;  // mask * value: masked positions are +0 (or -0*... the reference
+    bool bad = false;
+    if (mean) {
+      const long long s = spk[b];
+      bad = (unsigned long long)s >= (unsigned long long)n_rows;  // the reference raises IndexError: NaN marks the row
+      if (!bad) r = __fadd_rn(mean[s], __fmul_rn(r, stdv[s]));
+    }
+    out[i] = bad ? __int_as_float(0x7fc00000) : ((t < n && cls[i] > 0.f) ? r : 0.f);  // mask * value: masked positions are +0 (or -0*... the reference
                                                  // yields 0*r = +-0; both compare equal and print as 0.0/-0.0)
   }
 }
@@ -165,7 +171,8 @@ using namespace dissc;
 
 struct dissc_pred {
   int kind = 0;  // DISSC_PRED_LEN / _PITCH_NEW / _PITCH_BASE
-  int device = 0, E = 32, n_tokens = 0, n_speakers = 0, pe_len = 0;
+  int device = 0, E = 32, n_tokens = 0, n_speakers = 0, pe_len = 0, spk_rows = 0;
+  dissc::ErrFlag err;  // out-of-range token / speaker ids (dissc_pred_status)
   std::vector<void*> allocs;
   float* tok_w = nullptr;
   float* spk_w = nullptr;
@@ -246,6 +253,11 @@ int dissc_pred_create(dissc_pred_t** out, int kind, int n_tokens, int n_speakers
   *out = nullptr;
   DISSC_CHECK(kind == DISSC_PRED_LEN || kind == DISSC_PRED_PITCH_NEW || kind == DISSC_PRED_PITCH_BASE, DISSC_EINVAL,
               "unknown predictor kind %d", kind);
+  struct DeviceGuard {   // the caller's current device is restored on every exit path
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  cudaGetDevice(&guard.prev);
   DISSC_CUDA(cudaSetDevice(device));
   PredWeights wm;
   for (int i = 0; i < n_weights; ++i) wm.m[weights[i].name] = &weights[i];
@@ -263,6 +275,8 @@ int dissc_pred_create(dissc_pred_t** out, int kind, int n_tokens, int n_speakers
   if (tok->numel % (n_tokens + 1) || spk->numel % spk_rows || tok->numel / (n_tokens + 1) != spk->numel / spk_rows)
     return fail(set_err(DISSC_EINVAL, "embedding tables do not match n_tokens=%d n_speakers=%d", n_tokens, n_speakers));
   g->E = (int)(tok->numel / (n_tokens + 1));
+  g->spk_rows = spk_rows;
+  if ((rc = err_flag_create(&g->err))) return fail(rc);
   if ((rc = pred_upload(g, tok->data, tok->numel, &g->tok_w))) return fail(rc);
   if ((rc = pred_upload(g, spk->data, spk->numel, &g->spk_w))) return fail(rc);
   if (kind == DISSC_PRED_PITCH_NEW) {
@@ -296,9 +310,18 @@ int dissc_pred_create(dissc_pred_t** out, int kind, int n_tokens, int n_speakers
 
 void dissc_pred_destroy(dissc_pred_t* g) {
   if (!g) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(g->device);
   for (void* p : g->allocs) cudaFree(p);
+  err_flag_destroy(&g->err);
   delete g;
+  if (prev >= 0) cudaSetDevice(prev);
+}
+
+int dissc_pred_status(dissc_pred_t* g) {
+  DISSC_CHECK(g, DISSC_EINVAL, "null handle");
+  return err_flag_take(&g->err, "predictor forward", g->n_tokens + 1, g->spk_rows);
 }
 
 int dissc_pred_workspace_bytes(const dissc_pred_t* g, int B, int L, size_t* bytes) {
@@ -315,7 +338,7 @@ static int pred_trunk(dissc_pred* g, const int64_t* seq, const int64_t* spk, con
   const long long tot = (long long)B * 2 * g->E * L;
   pred_embed_kernel<<<(int)std::min<long long>((tot + 255) / 256, 148 * 8), 256, 0, st>>>(
       reinterpret_cast<const long long*>(seq), reinterpret_cast<const long long*>(spk), lengths, g->tok_w, g->spk_w,
-      g->pe, g->E, B, L, bufs[0]);
+      g->pe, g->E, B, L, bufs[0], g->n_tokens + 1, g->spk_rows, g->err.dev);
   DISSC_CUDA(cudaGetLastError());
   int cur = 0;
   for (const PredConv& c : g->trunk) {
@@ -335,7 +358,7 @@ static int pred_check(dissc_pred* g, const void* seq, const void* spk, int B, in
   int dev = -1;
   DISSC_CUDA(cudaGetDevice(&dev));
   DISSC_CHECK(dev == g->device, DISSC_EINVAL, "current device %d != handle device %d", dev, g->device);
-  return DISSC_OK;
+  return err_flag_take(&g->err, "an earlier predictor forward", g->n_tokens + 1, g->spk_rows);
 }
 
 int dissc_len_forward(dissc_pred_t* g, const int64_t* seq, const int64_t* spk, const int32_t* lengths, int B, int L,
@@ -375,12 +398,13 @@ int dissc_pitch_forward(dissc_pred_t* g, const int64_t* seq, const int64_t* spk,
 }
 
 int dissc_pitch_calc_freq(const float* cls, const float* reg, const int64_t* spk, const float* mean, const float* std,
-                          const int32_t* lengths, int B, int L, float* out, void* stream) {
+                          int n_stats_rows, const int32_t* lengths, int B, int L, float* out, void* stream) {
   DISSC_CHECK(cls && reg && out && B > 0 && L > 0, DISSC_EINVAL, "bad argument");
   DISSC_CHECK((mean == nullptr) == (std == nullptr) && (mean == nullptr || spk != nullptr), DISSC_EINVAL,
               "mean/std must both be given (with spk) or both NULL (normalised output)");
+  DISSC_CHECK(mean == nullptr || n_stats_rows > 0, DISSC_EINVAL, "n_stats_rows=%d must be the length of mean/std", n_stats_rows);
   pitch_calc_freq_kernel<<<std::min((B * L + 255) / 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      cls, reg, reinterpret_cast<const long long*>(spk), mean, std, lengths, B, L, out);
+      cls, reg, reinterpret_cast<const long long*>(spk), mean, std, n_stats_rows, lengths, B, L, out);
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }

@@ -36,7 +36,9 @@ struct Pair64Params {
   const __half* w2;
   const float* b1;      // [64]
   const float* b2;
-  float inv1, inv2;     // 2^-s of the two weight scalings
+  float inv1, inv2;     // 2^-s of the two weight scalings, with 1 / in_scale resp. 1 / xt_scale folded in by the host
+  float in_scale, xt_scale, plane_scale;  // power-of-two activation scales (TcParams): the input planes, the on-chip xt
+                                          // tile and the output planes hold value * scale
   float in_inv_slope;   // 1 / in_slope: x = min(y, y * in_inv_slope)
   const float* acc_in;  // f32b [B][8][Tr][8] or null (MRF accumulator xs)
   float* out_f;         // f32b or null
@@ -205,7 +207,8 @@ __global__ void __launch_bounds__(kPair64Threads, 1) resblock_pair64_tc_kernel(c
     unsigned char* xt = sXt + g * xt_bytes;
     const uint32_t t_acc1 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * 256u;
     const uint32_t t_acc2 = t_acc1 + 128u;
-    const float slope = p.plane_slope, inv_in = p.in_inv_slope;
+    const float slope = p.plane_slope;
+    const float un_in = 1.f / p.in_scale, inv_in = p.in_inv_slope * un_in;   // residual: x = min(y, y / slope) / in_scale
     uint32_t it = 0;
     const int first = blockIdx.x + g * gridDim.x, step = 2 * gridDim.x;
     for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(kPair64Threads, 1) resblock_pair64_tc_kernel(c
             if (v_ok) {
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = leaky((m[q][e] + x8[q][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f);
+              for (int e = 0; e < 8; ++e) v[e] = leaky((m[q][e] + x8[q][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f) * p.xt_scale;
               split_store8(reinterpret_cast<__half*>(xt + o), reinterpret_cast<__half*>(xt + xt_plane + o), v);
             } else {
               *reinterpret_cast<uint4*>(xt + o) = make_uint4(0, 0, 0, 0);
@@ -301,8 +304,8 @@ __global__ void __launch_bounds__(kPair64Threads, 1) resblock_pair64_tc_kernel(c
               const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hh[e]));
               const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ll[e]));
               const float y0 = fh.x + fl.x, y1 = fh.y + fl.y;
-              v[2 * e] = fminf(y0, y0 * inv_in);          // inverse leaky-relu: x = y (y >= 0), y / slope (y < 0)
-              v[2 * e + 1] = fminf(y1, y1 * inv_in);
+              v[2 * e] = fminf(y0 * un_in, y0 * inv_in);          // inverse leaky-relu: x = y (y >= 0), y / slope (y < 0)
+              v[2 * e + 1] = fminf(y1 * un_in, y1 * inv_in);
             }
           }
 #pragma unroll
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(kPair64Threads, 1) resblock_pair64_tc_kernel(c
           if (p.out_hi) {
             float a[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = leaky(v[e], slope);
+            for (int e = 0; e < 8; ++e) a[e] = leaky(v[e], slope) * p.plane_scale;
             split_store8(p.out_hi + po, p.out_lo + po, a);
           }
         }

@@ -42,7 +42,9 @@ struct PairParams {
   const __half* w2;
   const float* b1;      // [C]
   const float* b2;
-  float inv1, inv2;     // 2^-s of the two weight scalings
+  float inv1, inv2;     // 2^-s of the two weight scalings, with 1 / in_scale resp. 1 / xt_scale folded in by the host
+  float in_scale, xt_scale, plane_scale;  // power-of-two activation scales (TcParams): the on-chip operand tile of
+                                          // lrelu(x), the xt tile and the output planes hold value * scale
   const float* acc_in;  // f32h or null (MRF accumulator xs)
   float* out_f;         // f32h or null
   __half* out_hi;       // planes [B][C/8][Tp][8] or null (leaky-relu(plane_slope) iff plane_act)
@@ -221,8 +223,9 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
           const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)item * 32);
           const float4 c = *reinterpret_cast<const float4*>(stg + (size_t)item * 32 + 16);
           float v[8];
-          v[0] = leaky(a.x, 0.1f); v[1] = leaky(a.y, 0.1f); v[2] = leaky(a.z, 0.1f); v[3] = leaky(a.w, 0.1f);
-          v[4] = leaky(c.x, 0.1f); v[5] = leaky(c.y, 0.1f); v[6] = leaky(c.z, 0.1f); v[7] = leaky(c.w, 0.1f);
+          const float si = p.in_scale;   // leaky(x) * s == leaky(x * s) for s > 0
+          v[0] = leaky(a.x * si, 0.1f); v[1] = leaky(a.y * si, 0.1f); v[2] = leaky(a.z * si, 0.1f); v[3] = leaky(a.w * si, 0.1f);
+          v[4] = leaky(c.x * si, 0.1f); v[5] = leaky(c.y * si, 0.1f); v[6] = leaky(c.z * si, 0.1f); v[7] = leaky(c.w * si, 0.1f);
           split_store8(reinterpret_cast<__half*>(xop + (size_t)item * 16),
                        reinterpret_cast<__half*>(xop + xop_plane + (size_t)item * 16), v);
         } else {
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
           if (v_ok) {
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = leaky((m[q][e] + x8[q][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f);
+            for (int e = 0; e < 8; ++e) v[e] = leaky((m[q][e] + x8[q][e]) * p.inv1 + s_b1[c8 * 8 + e], 0.1f) * p.xt_scale;
             split_store8(reinterpret_cast<__half*>(xt + o), reinterpret_cast<__half*>(xt + xt_plane + o), v);
           } else {
             *reinterpret_cast<uint4*>(xt + o) = make_uint4(0, 0, 0, 0);
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(PairCfg<NC>::THREADS, (NC == 16) ? 2 : 1) resb
           if (out_valid) {
             float a[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = p.plane_act ? leaky(v[e], p.plane_slope) : v[e];
+            for (int e = 0; e < 8; ++e) a[e] = (p.plane_act ? leaky(v[e], p.plane_slope) : v[e]) * p.plane_scale;
             split_store8(p.out_hi + o, p.out_lo + o, a);
           } else {
             *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(0, 0, 0, 0);

@@ -147,6 +147,9 @@ def infer_sample(seqs, pitch, spk_id, name, out_path, len_model=None, pitch_mode
                                                              pitch_model, norm_pitch, return_lens=True)
     n = int(out_len[0].item())
     units = out_seq[0, :n].cpu().numpy().tolist()
+    for m in (len_model, pitch_model):
+        if m is not None:
+            m.check_indices(synchronize=False)   # the .cpu() above synchronised
     if pitch_model is not None:
         pitches = f0[0, :n].cpu().numpy().tolist()
     else:
@@ -261,6 +264,9 @@ def run(args, batch_size: int = 256):
             out_seq, f0, out_len, new_counts, dd_len = convert_batch(seqs, spk, args.n_tokens, len_model, pitch_model,
                                                                      args.norm_pitch, return_lens=True)
             out_seq, out_len = out_seq.cpu(), out_len.cpu()
+            for m in (len_model, pitch_model):
+                if m is not None:
+                    m.check_indices(synchronize=False)   # the .cpu() above synchronised
             f0 = None if f0 is None else f0.cpu()
             if morph:
                 new_counts, dd_len = new_counts.cpu().numpy(), dd_len.cpu().numpy()

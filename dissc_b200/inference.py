@@ -217,6 +217,7 @@ def vocode_items(generator: CodeGenerator, items: List[dict], device, spkr_overr
         y = generator.generate_int16(code.to(device), f0.to(device) if generator.f0 else None,
                                      spkr.to(device) if generator.multispkr else None, lengths=lengths.to(device))
         y = y.cpu().numpy()
+        generator.check_indices(synchronize=False)   # the .cpu() above synchronised: bad unit / speaker ids raise here
         for b, i in enumerate(idx):
             out[i] = y[b, :hop * n_frames[i]].copy()
     return out

@@ -337,6 +337,17 @@ class CodeGenerator(nn.Module):
             None if int16 else ptr(out), ptr(out) if int16 else None), "dissc_gen_forward_host")
         return out
 
+    def check_indices(self, synchronize=True):
+        """Raises ``IndexError`` if a unit / speaker id outside its embedding table reached the kernels since the last
+        check.  ``nn.Embedding`` (sr/models.py:128,133) raises at the call; here the forward is asynchronous, so the
+        gather stays inside the table, a device-visible flag is set and the error surfaces at this call, at the next
+        forward, or when ``forward_host`` returns."""
+        if self._handle is None:
+            return
+        if synchronize:
+            torch.cuda.synchronize(self._handle_device)
+        _lib.check(_lib.lib().dissc_gen_status(self._handle), "CodeGenerator")
+
     def set_tensor_cores(self, enable: bool, device=None) -> int:
         """Toggle the tcgen05 path (default on); returns how many stages now run on tensor cores."""
         dev = device or self._handle_device or torch.device("cuda", 0)

@@ -111,6 +111,16 @@ class _Predictor(nn.Module):
         return h, seq, spk, lengths, B, L, dev
 
 
+    def check_indices(self, synchronize=True):
+        """Raises ``IndexError`` if a token / speaker id outside its embedding table reached the kernels since the last
+        check (``nn.Embedding`` raises at the call; here the gather stays in bounds and a device-visible flag is set)."""
+        if self._handle is None:
+            return
+        if synchronize:
+            torch.cuda.synchronize(self._handle_device)
+        _lib.check(_lib.lib().dissc_pred_status(self._handle), "predictor")
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -170,7 +180,8 @@ class _PitchCommon(_Predictor):
             lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().dissc_pitch_calc_freq(_p(class_preds.contiguous()), _p(reg_preds.contiguous()), _p(spk),
-                                                        _p(mean), _p(std), _p(lengths), B, L, _p(out), _stream(dev)),
+                                                        _p(mean), _p(std), 0 if mean is None else mean.numel(),
+                                                        _p(lengths), B, L, _p(out), _stream(dev)),
                        "dissc_pitch_calc_freq")
         return out
 

@@ -47,19 +47,51 @@ def _wn_pair(gen, shape, fan_in, scale=1.0):
     return g, v
 
 
-def synthetic_generator_state_dict(h: dict, seed: int = 0, post_std: float = 0.5) -> dict:
+RECIPES = ("calibrated", "hot", "init_weights", "torch_default")
+
+
+def synthetic_generator_state_dict(h: dict, seed: int = 0, post_std: float = 0.5, recipe: str = "calibrated") -> dict:
     """Checkpoint-format (``weight_g``/``weight_v``/``bias``) state dict for
-    ``CodeGenerator(h)`` -- key set identical to what ``sr/train.py:206-214`` saves."""
+    ``CodeGenerator(h)`` -- key set identical to what ``sr/train.py:206-214`` saves.
+
+    ``recipe``:
+      * ``calibrated``    the O(1)-activation recipe described above (default; the benchmark weights);
+      * ``hot``           the same with 2x the ``convs2`` gain, 3x bias and a pre-tanh std of 1.2 (tanh saturates often);
+      * ``init_weights``  every conv weight ~ N(0, 0.01) as ``init_weights`` asks for (sr/utils.py:32-35), ``g = ||v||``,
+                          biases as ``nn.Conv1d`` initialises them, U(+-1/sqrt(fan_in)): activations shrink by orders of
+                          magnitude through the upsamplers (output std ~3e-3), which exercises the SMALL end of the
+                          split-fp16 operand range;
+      * ``torch_default`` what a freshly constructed reference ``Generator`` really holds (``init_weights`` writes the
+                          derived ``weight`` attribute that old-style weight-norm recomputes from g / v at the next forward,
+                          so the effective weights are ``nn.Conv1d``'s own kaiming-uniform init)."""
+    if recipe not in RECIPES:
+        raise ValueError(f"unknown recipe {recipe!r}; expected one of {RECIPES}")
     gen = torch.Generator().manual_seed(seed)
     sd = {}
     c0 = h["upsample_initial_channel"]
     cin = h.get("model_in_dim", 128)
+    hot = recipe == "hot"
+    if hot:
+        post_std = 1.2
 
     def put(prefix, shape, fan_in, scale=1.0):
+        nb = shape[1] if prefix.startswith("ups.") else shape[0]
+        if recipe in ("init_weights", "torch_default"):
+            torch_fan_in = shape[1] * shape[2]   # nn.init._calculate_fan_in_and_fan_out: size(1) * receptive field
+            bound = 1.0 / math.sqrt(torch_fan_in)
+            if recipe == "init_weights":
+                v = 0.01 * torch.randn(shape, generator=gen)
+            else:
+                v = (2 * torch.rand(shape, generator=gen) - 1) * bound   # kaiming_uniform_(a=sqrt(5))
+            g = v.reshape(shape[0], -1).norm(dim=1).reshape(shape[0], *([1] * (len(shape) - 1)))
+            sd[prefix + ".weight_g"], sd[prefix + ".weight_v"] = g, v
+            sd[prefix + ".bias"] = (2 * torch.rand(nb, generator=gen) - 1) * bound
+            return
+        if hot and ".convs2." in prefix:
+            scale *= 2.0
         g, v = _wn_pair(gen, shape, fan_in, scale)
         sd[prefix + ".weight_g"], sd[prefix + ".weight_v"] = g, v
-        nb = shape[1] if prefix.startswith("ups.") else shape[0]
-        sd[prefix + ".bias"] = 0.01 * torch.randn(nb, generator=gen)
+        sd[prefix + ".bias"] = (0.03 if hot else 0.01) * torch.randn(nb, generator=gen)
 
     put("conv_pre", (c0, cin, 7), cin * 7)
     ch = c0

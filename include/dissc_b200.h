@@ -36,6 +36,7 @@ extern "C" {
 #define DISSC_ECUDA (-3)        /* CUDA runtime error (message has the cudaError string) */
 #define DISSC_ENOMEM (-4)
 #define DISSC_EMISSING (-5)     /* a required tensor is absent from the weight list */
+#define DISSC_EINDEX (-6)       /* a unit / speaker id outside its embedding table (nn.Embedding raises IndexError) */
 
 #define DISSC_MAX_STAGES 8
 #define DISSC_MAX_KERNELS 8
@@ -118,6 +119,28 @@ int dissc_gen_forward_i16(dissc_gen_t* g, const int64_t* code, const float* f0, 
 int dissc_gen_forward_host(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr,
                            const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16);
 
+/* Pipelined form of dissc_gen_forward_host: DISSC_HOST_SLOTS batches may be in flight.  _submit enqueues H2D ->
+ * forward -> D2H for `slot` and returns without waiting; _wait(slot) blocks until that slot's output is in the host
+ * buffer given to _submit (and reports out-of-range ids like dissc_gen_forward_host).  Submitting slot s+1 before
+ * waiting for slot s hides the copy-back of one batch under the forward of the next; host buffers of a slot must stay
+ * valid (and pinned, for the copies to be asynchronous) until its _wait returns.  Re-submitting a slot without
+ * waiting for it is allowed only if its output buffer may be overwritten.  dissc_gen_forward_host == submit(0) + wait(0).
+ * dissc_gen_host_reserve pre-sizes the device staging arena for (B,T) batches so that no call allocates (the arena
+ * otherwise grows on the first call that needs more). */
+#define DISSC_HOST_SLOTS 2
+int dissc_gen_forward_host_submit(dissc_gen_t* g, int slot, const int64_t* code, const float* f0, const int64_t* spkr,
+                                  const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16);
+int dissc_gen_forward_host_wait(dissc_gen_t* g, int slot);
+int dissc_gen_host_reserve(dissc_gen_t* g, int B, int T);
+
+/* Unit and speaker ids are range-checked on the device (nn.Embedding raises IndexError / a device assert on an id
+ * outside its table, sr/models.py:128,133,189,213): a bad id never reads outside the table (row 0 is used), and it sets
+ * a per-handle flag.  dissc_gen_status returns DISSC_EINDEX (and clears the flag) if any forward enqueued through this
+ * handle so far saw one -- it does not synchronise, so synchronise the stream first for a definitive answer.
+ * dissc_gen_forward_host checks after its own synchronisation; dissc_gen_forward{,_i16} check on entry (i.e. report a
+ * bad id of the PREVIOUS batch at the latest). */
+int dissc_gen_status(dissc_gen_t* g);
+
 /* The ResBlock stages whose geometry allows it (C in {16,32,64,128,256}, padding <= 32) run on the tcgen05
  * tensor cores with split-fp16 operands (fp32-accurate); when every stage does, conv_pre and the
  * transposed convs run there too.  The others, and everything when disabled, use the fp32 CUDA-core kernels.
@@ -166,6 +189,9 @@ int dissc_pred_create(dissc_pred_t** out, int kind, int n_tokens, int n_speakers
                       int n_weights, int device);
 void dissc_pred_destroy(dissc_pred_t* g);
 int dissc_pred_workspace_bytes(const dissc_pred_t* g, int B, int L, size_t* bytes);
+/* Same contract as dissc_gen_status for token ids (rows n_tokens + 1) and speaker ids of the predictors
+ * (nn.Embedding at model/len_predictor.py:15-16, model/pitch_predictor.py:51-52). */
+int dissc_pred_status(dissc_pred_t* g);
 
 /* Replaces: len_model(dd_seq, spk_id)  (infer.py:30 -> LenPredictor.forward model/len_predictor.py:35-52), batched:
  * seq int64 (B,L) deduplicated units, spk int64 (B), lengths int32 (B) valid tokens per row (NULL = L; rows behave like
@@ -179,9 +205,10 @@ int dissc_pitch_forward(dissc_pred_t* g, const int64_t* seq, const int64_t* spk,
                         float* cls, float* reg, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Replaces: calc_freq  (model/pitch_predictor.py:100-104): out = (cls > 0) * (mean[spk] + reg * std[spk]), or
- * (cls > 0) * reg when mean == std == NULL (norm=True).  mean/std are DEVICE arrays indexed by speaker id. */
+ * (cls > 0) * reg when mean == std == NULL (norm=True).  mean/std are DEVICE arrays of n_stats_rows entries indexed by
+ * speaker id; a speaker id outside [0, n_stats_rows) (the reference raises IndexError) yields NaN for that row. */
 int dissc_pitch_calc_freq(const float* cls, const float* reg, const int64_t* spk, const float* mean, const float* std,
-                          const int32_t* lengths, int B, int L, float* out, void* stream);
+                          int n_stats_rows, const int32_t* lengths, int B, int L, float* out, void* stream);
 
 /* Replaces: len_carryover_correction  (infer.py:158-172), batched.  lens fp32 (B,L) -> out int32 (B,L) (0 past the
  * valid length), totals int32 (B) = sum of the corrected lengths (may be NULL).  Bit-exact: fp32 running sum,

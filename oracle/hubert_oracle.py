@@ -7,8 +7,11 @@ file restates the published fairseq graph (fairseq/models/hubert/hubert.py ``Hub
 fairseq/models/wav2vec/wav2vec2.py ``ConvFeatureExtractionModel`` mode "default", ``TransformerEncoder`` with
 ``layer_norm_first=False``, ``TransformerSentenceEncoderLayer`` post-LN; textless ``HubertFeatureReader.get_features``:
 no input normalisation for the base model, ``output_layer=6``; ``KMeansQuantizer``: nearest centroid) over a plain
-state dict with fairseq's parameter names.  tests/test_hubert_oracle.py cross-checks it against the independent
-implementation in ``torchaudio.models.hubert_base`` (random weights).
+state dict with fairseq's parameter names.  tests/test_hubert_oracle.py cross-checks it against TWO independent
+implementations of the same published architecture, each with its own random initialisation:
+``torchaudio.models.hubert_base`` and Hugging Face ``transformers.HubertModel`` (``hidden_states[6]``), at 6 000,
+96 000 and 160 000 samples; tests/golden/hubert_hf_small.npz pins a few output rows of the transformers model so the
+GPU box re-checks the same numbers.
 """
 from __future__ import annotations
 
@@ -63,6 +66,40 @@ def from_torchaudio(model, n_layers: int = 6) -> dict:
         sd[p + "fc2.bias"] = layer.feed_forward.output_dense.bias.detach().clone()
         sd[p + "final_layer_norm.weight"] = layer.final_layer_norm.weight.detach().clone()
         sd[p + "final_layer_norm.bias"] = layer.final_layer_norm.bias.detach().clone()
+    return sd
+
+
+def from_transformers(model, n_layers: int = 6) -> dict:
+    """State dict of a Hugging Face ``transformers.HubertModel`` (config = hubert-base: group-norm extractor,
+    ``do_stable_layer_norm=False``) under fairseq's names -- the inverse of transformers'
+    ``convert_hubert_original_pytorch_checkpoint_to_pytorch.py`` mapping -- pos_conv weight-norm (dim 2) folded.
+    A SECOND independent implementation of the published graph to check this oracle against."""
+    hf = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sd = {}
+    for i in range(7):
+        sd[f"feature_extractor.conv_layers.{i}.0.weight"] = hf[f"feature_extractor.conv_layers.{i}.conv.weight"]
+    sd["feature_extractor.conv_layers.0.2.weight"] = hf["feature_extractor.conv_layers.0.layer_norm.weight"]
+    sd["feature_extractor.conv_layers.0.2.bias"] = hf["feature_extractor.conv_layers.0.layer_norm.bias"]
+    sd["layer_norm.weight"], sd["layer_norm.bias"] = hf["feature_projection.layer_norm.weight"], hf["feature_projection.layer_norm.bias"]
+    sd["post_extract_proj.weight"] = hf["feature_projection.projection.weight"]
+    sd["post_extract_proj.bias"] = hf["feature_projection.projection.bias"]
+    pc = "encoder.pos_conv_embed.conv."
+    if pc + "weight_g" in hf:
+        g, v = hf[pc + "weight_g"], hf[pc + "weight_v"]
+    else:
+        g, v = hf[pc + "parametrizations.weight.original0"], hf[pc + "parametrizations.weight.original1"]
+    sd["encoder.pos_conv.0.weight"] = fold_pos_conv_weight_norm(g, v)
+    sd["encoder.pos_conv.0.bias"] = hf[pc + "bias"]
+    sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"] = hf["encoder.layer_norm.weight"], hf["encoder.layer_norm.bias"]
+    for l in range(n_layers):
+        p, q = f"encoder.layers.{l}.", f"encoder.layers.{l}."
+        for name in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[p + f"self_attn.{name}.weight"] = hf[q + f"attention.{name}.weight"]
+            sd[p + f"self_attn.{name}.bias"] = hf[q + f"attention.{name}.bias"]
+        sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"] = hf[q + "layer_norm.weight"], hf[q + "layer_norm.bias"]
+        sd[p + "fc1.weight"], sd[p + "fc1.bias"] = hf[q + "feed_forward.intermediate_dense.weight"], hf[q + "feed_forward.intermediate_dense.bias"]
+        sd[p + "fc2.weight"], sd[p + "fc2.bias"] = hf[q + "feed_forward.output_dense.weight"], hf[q + "feed_forward.output_dense.bias"]
+        sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"] = hf[q + "final_layer_norm.weight"], hf[q + "final_layer_norm.bias"]
     return sd
 
 

@@ -71,6 +71,66 @@ def test_vs_oracle_seeded(cuda_device, vctk_gen, B, T):
     assert err < TOL, err
 
 
+# BASELINE configs[1] geometry (T = 300 units -> 96 000 samples per utterance; the benched batch is 64 such rows and
+# rows are independent, test_config2_shape_properties) against the oracle, on the benchmark weights and on four other
+# seeds / weight recipes.  Absolute bound: the north-star's 1e-4 max-abs vs the fp32 oracle.  Relative bound: max-abs
+# error vs the fp64 oracle <= 4e-4 of the waveform's standard deviation -- the `init_weights` / `torch_default` recipes
+# produce waveforms with std 2e-4 / 2e-2, where an absolute 1e-4 says nothing (the fp32 oracle's own distance to fp64
+# on `init_weights` is 5e-5 of std).
+@pytest.mark.parametrize("seed,recipe,B", [(0, "calibrated", 8), (11, "calibrated", 4), (12, "hot", 4),
+                                           (13, "init_weights", 4), (14, "torch_default", 4)])
+def test_config2_rows_vs_oracle(cuda_device, seed, recipe, B):
+    from oracle import generator_oracle as go
+    T = 300
+    sd = syn.synthetic_generator_state_dict(syn.VCTK_CONFIG, seed=seed, recipe=recipe)
+    gen = make_generator(syn.VCTK_CONFIG, sd, cuda_device)
+    code, f0, spkr = syn.synthetic_inputs(B, T, seed=1234 + seed)   # seed 1234 = bench.py's rank-0 batch
+    y = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device)).cpu()
+    assert tuple(y.shape) == (B, 1, 320 * T) and torch.isfinite(y).all()
+    ref32 = go.code_generator_forward(sd, syn.VCTK_CONFIG, code, f0, spkr)
+    ref64 = go.code_generator_forward(sd, syn.VCTK_CONFIG, code, f0, spkr, dtype=torch.float64)
+    err32 = (y - ref32).abs().max().item()
+    err64 = (y.double() - ref64).abs().max().item()
+    std = ref64.std().item()
+    print(f"{recipe}/{seed}: max-abs vs fp32 oracle {err32:.2e}, vs fp64 {err64:.2e}, waveform std {std:.2e}, "
+          f"relative {err64 / std:.2e}")
+    assert err32 < TOL, err32
+    assert err64 / std < 4e-4, (err64, std)
+
+
+def test_out_of_range_ids_raise(cuda_device, vctk_gen):
+    """nn.Embedding raises IndexError for an id outside its table (sr/models.py:128,133); here the gather stays in
+    bounds, the forward completes, and the error surfaces at the next host-synchronous point."""
+    gen, _ = vctk_gen
+    code, f0, spkr = syn.synthetic_inputs(2, 20, seed=9)
+    good = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    gen.check_indices()
+    for bad_code, bad_spkr, word in ((100, None, "unit"), (-1, None, "unit"), (None, 200, "speaker"), (None, -7, "speaker")):
+        c2, s2 = code.clone(), spkr.clone()
+        if bad_code is not None:
+            c2[1, 3] = bad_code
+        if bad_spkr is not None:
+            s2[0, 0] = bad_spkr
+        y = gen(code=c2.to(cuda_device), f0=f0.to(cuda_device), spkr=s2.to(cuda_device))
+        assert torch.isfinite(y).all()          # the gather read row 0, not stray memory
+        with pytest.raises(IndexError, match=word):
+            gen.check_indices()
+        gen.check_indices()                      # the flag is cleared by the report
+        with pytest.raises(IndexError, match=word):   # host entry: reported by the call itself
+            gen.forward_host(c2.pin_memory(), f0.reshape(2, 20).contiguous().pin_memory(),
+                             s2.reshape(2).contiguous().pin_memory())
+    y = gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    gen.check_indices()
+    assert torch.equal(y, good)
+    # a bad id left unchecked is reported by the NEXT forward at the latest
+    c2 = code.clone()
+    c2[0, 0] = 12345
+    gen(code=c2.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device))
+
+
 def test_int16_and_host_entry(cuda_device, vctk_gen):
     """generate() of sr/inference.py:67-76 fused: int16 = trunc(y*32768) wrapped; host entry = same bits."""
     gen, _ = vctk_gen

@@ -1,5 +1,7 @@
-"""CPU: the HuBERT oracle (oracle/hubert_oracle.py) against the independent torchaudio implementation of the same
-published architecture (random weights).  The real textless/fairseq code is not available offline -> parity unpinned."""
+"""CPU: the HuBERT oracle (oracle/hubert_oracle.py) against TWO independent implementations of the same published
+architecture (torchaudio's and Hugging Face transformers', each with its own random weights) and against the committed
+rows of the transformers model (tests/golden/hubert_hf_small.npz).  The reference's own encoder (textlesslib / fairseq)
+is third-party code that is not available offline, so it cannot generate vectors itself."""
 import numpy as np
 import pytest
 import torch
@@ -33,6 +35,44 @@ def test_oracle_matches_torchaudio_layer6(ta_model):
     got = ho.extract_features(sd, wave, 6)
     assert got.shape == ref.shape == (2, ho.num_frames(6000), 768)
     assert (got - ref).abs().max().item() < 2e-4
+
+
+@pytest.fixture(scope="module")
+def hf_model():
+    pytest.importorskip("transformers")
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_hubert as mg
+    return mg, mg.build_model()
+
+
+@pytest.mark.parametrize("n", [6000, 96000, 160000])
+def test_oracle_matches_transformers_layer6(hf_model, n):
+    """Second independent graph: transformers.HubertModel hidden_states[6], incl. BASELINE configs[3]'s clip
+    lengths (96 000 samples, varlen up to 160 000)."""
+    mg, model = hf_model
+    sd = ho.from_transformers(model, 6)
+    g = torch.Generator().manual_seed(n)
+    wave = 0.1 * torch.randn(1, n, generator=g)
+    with torch.no_grad():
+        ref = model(wave, output_hidden_states=True).hidden_states[6]
+    got = ho.extract_features(sd, wave, 6)
+    assert got.shape == ref.shape == (1, ho.num_frames(n), 768)
+    assert (got - ref).abs().max().item() < 5e-5
+
+
+def test_oracle_matches_committed_transformers_rows(hf_model):
+    from _util import load_golden
+    mg, model = hf_model
+    gold = load_golden("hubert_hf_small.npz")
+    if abs(mg.weights_checksum(model) - float(gold["checksum"])) > 1e-6 * float(gold["checksum"]):
+        pytest.skip("this torch build initialises HubertModel differently from the one that wrote the fixture")
+    sd = ho.from_transformers(model, 6)
+    for n, w in mg.waves().items():
+        assert np.array_equal(w[0, :8].numpy(), gold[f"wave_head_{n}"])
+        got = ho.extract_features(sd, w, 6)[0][gold[f"rows_{n}"]]
+        assert np.abs(got.numpy() - gold[f"feat_{n}"]).max() < 5e-5
 
 
 def test_pos_conv_weight_norm_fold(ta_model):

@@ -153,16 +153,18 @@ def test_unsupported_geometry_fails_loudly(cuda_device):
 # tensor-core (tcgen05, split-fp16) twin of the fused conv
 # ---------------------------------------------------------------------------------------------
 def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0, wscale=1.0, Cin=None, tol=2e-5,
-             single_acc=False):
+             single_acc=False, xscale=1.0):
+    """xscale multiplies every activation-like input (x, bias, residual, accumulator): the op is positively homogeneous,
+    so the expected output scales by the same factor and the tolerance is relative to it."""
     from dissc_b200 import _lib
     _lib.lib().dissc_tc_set_single_accumulator(int(single_acc))
     g = torch.Generator().manual_seed(seed)
     Cin = Cin or C
-    x = torch.randn(B, Cin, T, generator=g)
+    x = xscale * torch.randn(B, Cin, T, generator=g)
     w = wscale * torch.randn(C, Cin, k, generator=g) / (Cin * k) ** 0.5
-    b = torch.randn(C, generator=g)
-    r = torch.randn(B, C, T, generator=g) if res else None
-    a = torch.randn(B, C, T, generator=g) if acc else None
+    b = xscale * torch.randn(C, generator=g)
+    r = xscale * torch.randn(B, C, T, generator=g) if res else None
+    a = xscale * torch.randn(B, C, T, generator=g) if acc else None
     xin = x.clone()
     if lengths is not None:
         for i, n in enumerate(lengths):
@@ -191,7 +193,7 @@ def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0,
                                                _ptr(outs[1]), _ptr(outs[2]), _ptr(ld), 1, B, Cin, C, T, k, d, int(pre), 0.1,
                                                int(post), 0.01, float(div), None))
     torch.cuda.synchronize()
-    scale = max(1.0, wscale)
+    scale = max(1.0, wscale) * xscale
     _lib.lib().dissc_tc_set_single_accumulator(1)  # library default
     for name, got, want in (("plain", outs[0].cpu(), y), ("raw", outs[1].cpu(), raw), ("planes", outs[2].cpu(), y)):
         got = got.clone()
@@ -248,6 +250,19 @@ def test_tc_conv_lengths_mask(cuda_device):
 def test_tc_conv_weight_scaling(cuda_device, wscale):
     # the power-of-two pre-scale keeps the fp16 split accurate whatever the weight magnitude
     _tc_case(cuda_device, 1, 64, 300, 7, 1, pre=False, post=False, res=False, acc=False, div=0, wscale=wscale)
+
+
+# Dynamic range of the split-fp16 ACTIVATION planes (the weights carry their own power-of-two scale): fp16 is normal
+# on [6.1e-5, 65504] and the `lo` plane needs |x| >= 2^-3 for all of its 11 bits, so an unscaled plane loses relative
+# precision once a whole tensor sits below ~0.1 and saturates above 6.5e4.  The layer entry points measure nothing:
+# they scale the planes by the power of two `plane_scale_for(absmax)` of the tensor they pack (the model does the same
+# per layer at load time, DESIGN.md "Activation scale"), so every magnitude below keeps the fp32-class relative error.
+@pytest.mark.parametrize("xscale", [1e-4, 1e-2, 1.0, 1e2, 1e3, 3e4])
+def test_tc_conv_activation_scale_sweep(cuda_device, xscale):
+    _tc_case(cuda_device, 2, 64, 515, 7, 3, pre=True, post=True, res=True, acc=True, div=3.0, xscale=xscale)
+    _tc_case(cuda_device, 1, 256, 300, 11, 1, pre=True, post=True, res=True, acc=False, div=0, xscale=xscale, tol=1e-4,
+             single_acc=True)
+    _tc_case(cuda_device, 2, 16, 2500, 3, 1, pre=True, post=False, res=False, acc=False, div=0, xscale=xscale)
 
 
 @pytest.mark.parametrize("Cin,Cout", [(257, 512), (17, 32), (40, 16), (272, 256)])
@@ -310,14 +325,14 @@ def test_tc_conv_transpose1d_lengths(cuda_device):
 # ---------------------------------------------------------------------------------------------
 # fused ResBlock pair (resblock_tc.cuh)
 # ---------------------------------------------------------------------------------------------
-def _pair_case(dev, B, C, T, k, d, acc=False, div=0.0, lengths=None, seed=0):
+def _pair_case(dev, B, C, T, k, d, acc=False, div=0.0, lengths=None, seed=0, xscale=1.0):
     from dissc_b200 import _lib
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(B, C, T, generator=g)
+    x = xscale * torch.randn(B, C, T, generator=g)
     w1 = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
     w2 = 0.5 * torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
-    b1, b2 = torch.randn(C, generator=g), torch.randn(C, generator=g)
-    a = torch.randn(B, C, T, generator=g) if acc else None
+    b1, b2 = xscale * torch.randn(C, generator=g), xscale * torch.randn(C, generator=g)
+    a = xscale * torch.randn(B, C, T, generator=g) if acc else None
     outs = []
     for b in range(B):   # reference semantics: every utterance alone, unpadded
         n = T if lengths is None else lengths[b]
@@ -350,14 +365,21 @@ def _pair_case(dev, B, C, T, k, d, acc=False, div=0.0, lengths=None, seed=0):
             assert torch.all(pl[i, :, n:] == 0), "rows past the valid length must be stored as zeros"
             raw[i, :, n:] = 0
     assert torch.isfinite(raw).all() and torch.isfinite(pl).all()
-    assert (raw - want).abs().max().item() < 3e-5
-    assert (pl - F.leaky_relu(want, 0.1)).abs().max().item() < 3e-5
+    assert (raw - want).abs().max().item() < 3e-5 * xscale
+    assert (pl - F.leaky_relu(want, 0.1)).abs().max().item() < 3e-5 * xscale
 
 
 @pytest.mark.parametrize("C", [16, 32, 64])
 @pytest.mark.parametrize("k,d", [(3, 1), (3, 3), (3, 5), (7, 1), (7, 3), (7, 5), (11, 1), (11, 3), (11, 5)])
 def test_pair_resblock_shapes(cuda_device, C, k, d):
     _pair_case(cuda_device, 2, C, 1000, k, d)
+
+
+@pytest.mark.parametrize("xscale", [1e-4, 1e-2, 1e2, 1e3, 3e4])
+@pytest.mark.parametrize("C", [16, 32, 64])
+def test_pair_activation_scale_sweep(cuda_device, C, xscale):
+    _pair_case(cuda_device, 2, C, 700, 7, 3, acc=True, div=3.0, xscale=xscale)
+    _pair_case(cuda_device, 2, C, 700, 11, 1, xscale=xscale)
 
 
 @pytest.mark.parametrize("T", [1, 2, 117, 118, 119, 128, 1025])
