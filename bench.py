@@ -8,9 +8,13 @@ batch 64 VCTK-shape utterances x 300 units (96 000 samples each), per GPU
 (weak scaling: every rank vocodes its own 64-utterance shard, no data-path
 collective).  A step = one forward over one batch.
 
-  value   device-resident inputs, CUDA-event time, max over ranks
-  e2e     the C-ABI host call (dissc_gen_forward_host): pinned host inputs ->
-          H2D -> forward -> D2H waveform, every step inside the timed region
+  value    device-resident inputs, CUDA-event time, max over ranks
+  e2e      the C-ABI host entry (dissc_gen_forward_host_submit / _wait): pinned host
+           inputs -> H2D -> forward -> D2H waveform, every step inside the timed region
+  gathered the N-GPU data path: rank 0 owns inputs and outputs; one packed NCCL
+           scatter -> forward -> NCCL gather of the int16 waveforms (overlapped)
+  configs  short runs of BASELINE configs[2..4] (prosody -> vocode, HuBERT units,
+           encode -> predict -> vocode) on this rank's shard
   roofline / cpu_baseline: see DESIGN.md "Measurement"
 
 `--impl reference` times the reference's CPU path (the oracle port of
@@ -36,6 +40,7 @@ METRIC = "16kHz audio samples/sec vocoded"
 UNIT = "samples/s"
 B_PER_GPU, T_UNITS, HOP = 64, 300, 320
 CPU_SAMPLE_B = 4
+TRAFFIC_FILE = "r02_traffic.json"   # ncu launch list of one forward of the CURRENT kernels (scripts/ncu_traffic.py)
 
 
 def measured_peaks():
@@ -135,6 +140,11 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU (default = BASELINE config 2)")
     ap.add_argument("--units", type=int, default=T_UNITS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2..4] sub-records")
+    ap.add_argument("--settle", type=float, default=1.5,
+                    help="seconds of untimed back-to-back forwards before the first timed region (on top of --warmup): "
+                         "under its power cap the chip's clock keeps sinking for the first second or two of sustained "
+                         "load, so without this the phase measured first (value) looks ~2%% faster than the later ones")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -147,20 +157,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: dissc_b200 has no CPU path")
     # NCCL may print its version banner on stdout when the first communicator is created: keep stdout to the ONE JSON
-    # line by pointing fd 1 at stderr until the communicator exists
+    # line by pointing fd 1 at stderr until the line itself is printed
     sys.stdout.flush()
     saved_fd = os.dup(1)
     os.dup2(2, 1)
-    try:
-        rank, world, local = ddist.init_from_env()
-        if world > 1:
-            torch.cuda.set_device(local)
-            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
-            torch.cuda.synchronize()
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved_fd, 1)
-        os.close(saved_fd)
+    rank, world, local = ddist.init_from_env()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
+        torch.cuda.synchronize()
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     dev = torch.device("cuda", local)
@@ -189,6 +194,11 @@ def main():
     for _ in range(args.warmup):
         y = gen(code=code, f0=f0, spkr=spkr)
     torch.cuda.synchronize()
+    t_settle = time.perf_counter()
+    while time.perf_counter() - t_settle < args.settle:
+        for _ in range(5):
+            y = gen(code=code, f0=f0, spkr=spkr)
+        torch.cuda.synchronize()
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -205,39 +215,112 @@ def main():
     ms_step = ms_total / args.steps
     n_samples = y.shape[-1] * B
     value = world * n_samples / (ms_step * 1e-3)
+    gen.check_indices(synchronize=False)
 
     # ---- end to end through the C-ABI host entry (pinned host buffers) ----
+    # dissc_gen_forward_host_submit / _wait with two batches in flight: every step copies its inputs host -> device,
+    # runs the forward and copies the waveform device -> host; step i's copy-back rides under step i+1's forward.
     code_p, f0_p = code_h.pin_memory(), f0_h.reshape(B, T).contiguous().pin_memory()
     spkr_p = spkr_h.reshape(B).contiguous().pin_memory()
-    out_p = torch.empty((B, gen.hop * T), dtype=torch.float32).pin_memory()
-    for _ in range(2):
-        gen.forward_host(code_p, f0_p, spkr_p, out=out_p, device=local)
+    out_p = [torch.empty((B, gen.hop * T), dtype=torch.float32).pin_memory() for _ in range(2)]
+    gen.host_reserve(B, T, device=local)
+    for i in range(max(2, args.warmup)):
+        gen.forward_host(code_p, f0_p, spkr_p, out=out_p[i % 2], device=local)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        gen.forward_host(code_p, f0_p, spkr_p, out=out_p, device=local)  # synchronous: returns after the D2H
+    for i in range(args.steps):
+        gen.forward_host_submit(i % 2, code_p, f0_p, spkr_p, out=out_p[i % 2], device=local)
+        if i > 0:
+            gen.forward_host_wait((i - 1) % 2)       # step i-1's waveform is in host memory
+    gen.forward_host_wait((args.steps - 1) % 2)
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
     barrier()
     h2d = code_p.numel() * 8 + f0_p.numel() * 4 + spkr_p.numel() * 8
-    d2h = out_p.numel() * 4
+    d2h = out_p[0].numel() * 4
     e2e_val = world * n_samples / e2e_s
-    parity_e2e = bool(torch.equal(out_p, y.reshape(B, -1).cpu()))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return
-    # ---- roofline -------------------------------------------------------------------------
-    # Dominant kernel = conv_tc_kernel (every conv but conv_post).  achieved = the algorithmic bytes of its launches
-    # (layer-fused traffic model, SURVEY.md 8d / DESIGN.md) / their summed CUDA-event durations, measured on one extra
-    # forward with an event pair around every launch on the launching stream.  `forward` is the same figure for the
-    # whole step over the timed region.
-    flops, abytes = gen.cost(B, T, dev)
-    peak_gbs, sm_max_mhz, peak_src = measured_peaks()
+    y_host = y.reshape(B, -1).cpu()
+    parity_e2e = bool(torch.equal(out_p[0], y_host) and torch.equal(out_p[1], y_host))
+
+    # ---- the N-GPU data path of the north-star: rank 0 owns inputs and outputs -----------------------------------
+    # one packed NCCL scatter -> forward (int16 written by conv_post into the gather's send buffer) -> NCCL gather on a
+    # side stream, double-buffered against the next step (dissc_b200/dist.py::ScatterGatherPipeline).  At N = 1 the same
+    # pipeline runs without collectives, which is the denominator of its scaling efficiency.
+    def fwd_i16(c_, f_, s_, l_, out):
+        gen.generate_int16(c_, f_, s_, lengths=l_, out=out)
+
+    pipe = ddist.ScatterGatherPipeline(rank, world, dev, B, T, gen.hop, fwd_i16)
+    packed = None
+    if rank == 0:
+        cg, fg, sg = syn.synthetic_inputs(world * B, T, seed=99)
+        lg = torch.full((world * B,), T, dtype=torch.int32)
+        packed = ddist.pack_inputs(cg.to(dev), fg.reshape(world * B, T).to(dev), sg.reshape(world * B).to(dev), lg.to(dev),
+                                   world)
+    for _ in range(max(3, args.warmup)):
+        pipe.step(packed)
+    pipe.flush()
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(args.steps):
+        last = pipe.step(packed)
+    pipe.flush()                                    # the compute stream waits for the outstanding gathers
+    g1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_gath = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+    gathered = {"value": world * n_samples / (ms_gath * 1e-3), "unit": UNIT, "ms_per_step": ms_gath,
+                "scatter_bytes_per_step": int(world * pipe.row_bytes), "gather_bytes_per_step": int(world * n_samples * 2),
+                "collectives": "1 packed scatter + 1 int16 gather per step (NCCL), gather on a side stream / own "
+                               "communicator, double-buffered" if world > 1 else "none (N=1: same pipeline, no collective)",
+                "output": "int16 (N*B, hop*T) on rank 0"}
+    if rank == 0:
+        # rank 0's own rows of the gathered result = its local forward of the same inputs, bit for bit
+        want = gen.generate_int16(cg[:B].to(dev), fg[:B].reshape(B, T).to(dev), sg[:B].reshape(B).to(dev),
+                                  lengths=lg[:B].to(dev))
+        gathered["bit_identical_to_local_forward"] = bool(torch.equal(pipe.gathered[last][0], want))
+        if world > 1:   # and the last rank's rows = the forward of ITS inputs (run here)
+            want_l = gen.generate_int16(cg[-B:].to(dev), fg[-B:].reshape(B, T).to(dev), sg[-B:].reshape(B).to(dev),
+                                        lengths=lg[-B:].to(dev))
+            gathered["bit_identical_last_rank"] = bool(torch.equal(pipe.gathered[last][world - 1], want_l))
+
+    # ---- BASELINE configs[2..4]: short, bounded runs of the other configs on this rank's shard ---------------------
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    configs = {}
+    if not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        try:
+            import bench_configs as bc
+            lm, pm = bc.build_predictors(dev)
+            configs["configs[2]"] = bc.run_config3(gen, lm, pm, dev, rank, world, max_over_ranks, utts=256, iters=2)
+            enc, hsd = bc.build_encoder(dev)
+            configs["configs[3]"] = bc.run_config4(enc, hsd, dev, rank, world, max_over_ranks, clips=32, iters=3,
+                                                   tensor_peak_tflops=tensor_peak,
+                                                   cpu_leg=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+            configs["configs[4]"] = bc.run_config5(gen, lm, pm, enc, dev, rank, world, max_over_ranks, clips=32, iters=2)
+        except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
+            configs["error"] = repr(e)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_fd, 1)
+    os.close(saved_fd)
+    if rank != 0:
+        return
+    # ---- roofline -------------------------------------------------------------------------
+    # Dominant kernel = the kernel family with the largest share of the step.  The path is a dense contraction
+    # (85 FLOP/B): the tensor pipe binds, so `roofline` is quoted against the measured sustained tensor rate --
+    # achieved = 3 x the algorithmic FLOPs of the family's launches (three fp16 MMAs per fp32-accurate product)
+    # / their summed CUDA-event durations, measured on one extra forward with an event pair around every launch on the
+    # launching stream.  `hbm` keeps the algorithmic-bytes fraction BASELINE.json's metric asks for (same launches,
+    # layer-fused traffic model, SURVEY.md 8d / DESIGN.md), `forward` the whole step over the timed region.
+    flops, abytes = gen.cost(B, T, dev)
+    peak_gbs, sm_max_mhz, peak_src = measured_peaks()
     rows = gen.profile(code, f0, spkr)  # one extra, untimed forward with an event pair around every launch
     fam = {}
     for name, ms, fl, by in rows:
@@ -264,17 +347,21 @@ def main():
     dom_bytes = sum(r[3] for r in dom_rows)
     dom_ms = sum(r[1] for r in dom_rows)
     dom_flops = sum(r[2] for r in dom_rows)
-    ach = dom_bytes / (dom_ms * 1e-3) / 1e9
-    fwd_ach = abytes / (ms_step * 1e-3) / 1e9
+    n_dom = max(1, len(dom_rows))
+    ach_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
+    fwd_gbs = abytes / (ms_step * 1e-3) / 1e9
     split_tflops = 3.0 * dom_flops / (dom_ms * 1e-3) / 1e12   # three fp16 MMAs per fp32-accurate product
+    fwd_tflops = 3.0 * flops / (ms_step * 1e-3) / 1e12
     # measured DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel, from the
-    # committed ncu launch list of the same workload (scripts/ncu_traffic.py); null for other batch shapes
+    # committed ncu launch list of the same command on the current kernels (scripts/ncu_traffic.py); null otherwise
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_d_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
     if (B, T) == (B_PER_GPU, T_UNITS) and os.path.isfile(tpath):
-        tk = json.load(open(tpath))["kernels"].get(dom_name)
+        tj = json.load(open(tpath))
+        tk = tj["kernels"].get(dom_name)
         if tk and tk["launches"] == len(dom_rows):
-            traffic, traffic_src = tk["dram_bytes_per_launch"], "profiles/r01_d_traffic.json (ncu, one forward)"
+            traffic = tk["dram_bytes_per_launch"]
+            traffic_src = f"profiles/{TRAFFIC_FILE} (ncu launch list of one forward, {tj.get('commit', 'this round')})"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -282,31 +369,43 @@ def main():
         "config": {"workload": f"CodeGenerator forward, batch={B} VCTK-shape utterances x {T} units "
                                f"(x{gen.hop} -> {gen.hop * T} samples each) per GPU (BASELINE configs[1])",
                    "weights": "seeded synthetic checkpoint, shipped VCTK geometry (13.7M params)",
-                   "arithmetic": "fp32 results (<=2e-5 max-abs vs fp64) from split-fp16 tcgen05 MMAs, fp32 accumulate",
+                   "arithmetic": "fp32 results (<=1e-4 max-abs vs the oracle, tests/test_generator_gpu.py) from "
+                                 "split-fp16 tcgen05 MMAs, fp32 accumulate",
                    "l2": "every layer's working set (>=0.8 GB at B=64) exceeds the 126 MB L2; no flush needed",
                    "parallelism": f"utterance-sharded x{world}"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": "dissc_gen_forward_host (C ABI, pinned host buffers)",
+                "ms_per_step": e2e_s * 1e3,
+                "api": "dissc_gen_forward_host_submit / _wait (C ABI, pinned host buffers, two batches in flight: "
+                       "every step does H2D + forward + D2H, a step's D2H overlaps the next step's forward)",
                 "bit_identical_to_device_path": parity_e2e},
+        "gathered": gathered,
         "gpu_launches": gen.launches_per_forward() * args.steps,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "roofline": {"bound": "tensor", "achieved": split_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": split_tflops / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, sustained: the kernel is "
+                                    "timed inside a long step)",
                      "kernel": f"{dom_name} ({dom['launches']} of {len(rows)} launches per forward, "
                                f"{100 * dom['share']:.1f}% of the step)",
-                     "algorithmic_bytes_per_launch_avg": dom_bytes / max(1, len(dom_rows)),
-                     "launch_ms_avg": dom_ms / max(1, len(dom_rows)),
-                     "forward": {"achieved": fwd_ach, "frac": fwd_ach / peak_gbs, "algorithmic_bytes_per_step": abytes,
+                     "algorithmic_flops_per_launch_avg": dom_flops / n_dom,
+                     "mma_flops_per_launch_avg": 3.0 * dom_flops / n_dom,
+                     "algorithmic_bytes_per_launch_avg": dom_bytes / n_dom,
+                     "launch_ms_avg": dom_ms / n_dom,
+                     "why_tensor": "dense contraction, 85 FLOP/B algorithmic; three fp16 MMAs per fp32-accurate product "
+                                   "put the tensor floor (13.4 ms) above the HBM floor (11.1 ms); ncu: tensor pipe "
+                                   "80-94% busy in the k>=7 layers, DRAM 7-40% (profiles/README.md)",
+                     "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": peak_gbs, "unit": "GB/s",
+                             "frac": ach_gbs / peak_gbs, "peak_source": peak_src,
+                             "note": "same launches, algorithmic bytes of the layer-fused traffic model"},
+                     "forward": {"hbm": {"achieved": fwd_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": fwd_gbs / peak_gbs,
+                                         "algorithmic_bytes_per_step": abytes},
+                                 "tensor": {"achieved": fwd_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                                            "frac": fwd_tflops / tensor_peak, "algorithmic_flops_per_step": flops},
                                  "note": "whole step over the timed region (all kernels)"},
-                     "binding_roof": "tensor pipe (dense contraction, 85 FLOP/B; ncu: tensor pipe 83-94% busy in the "
-                                     "k>=7 layers of every stage): see tensor_pipe; measured DRAM traffic of a "
-                                     "forward is 39.9 GB (algorithmic 72.4 GB)",
-                     "tensor_pipe": {"achieved_tflops_fp32_equivalent": dom_flops / (dom_ms * 1e-3) / 1e12,
-                                     "achieved_tflops_fp16_mma": split_tflops, "peak_tflops": tensor_peak,
-                                     "frac": split_tflops / tensor_peak,
-                                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16)"},
                      "kernels": fam},
     }
+    if configs:
+        line["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
         val, ms, cores = cpu_port_time(CPU_SAMPLE_B, T, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",

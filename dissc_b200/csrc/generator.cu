@@ -26,6 +26,7 @@
 #include "tc_host.cuh"
 #include "resblock_tc.cuh"
 #include "resblock64_tc.cuh"
+#include "resblock_pack2_tc.cuh"
 
 namespace dissc {
 
@@ -196,17 +197,25 @@ static int launch_conv_post(const ConvPostParams& p, int k, cudaStream_t st) {
 // ------------------------------------------------------------------------
 // NC == 256: one accumulator (so TMEM double-buffers) instead of main+cross.  Measured end to end (profiles/README.md):
 // 1.8e-5 max-abs vs fp64 instead of 7e-6, stage 0 23 % faster.  DISSC_TC_SINGLE_ACC=0 restores the dual accumulator.
-static int g_single_acc256 = -1;
+static int g_single_acc256 = -1;   // -1: env DISSC_TC_SINGLE_ACC or the default (0)
 // plan-time tuning knobs (dissc_tc_set_tuning): activation buffers preferred by the streamed-weight layers, and whether
 // the N >= 128 kernels use their separate weight-producer thread
 static int g_tc_na_pref = -1, g_tc_split_w = 1;
+// 256-column GEMMs as two 128-column chunks (each with its own main + cross accumulators, double-buffered in TMEM)
+// instead of one 256-column chunk: -1 = env DISSC_TC_SPLIT256 or the default
+static int g_tc_split256 = -1;
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
 bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc) {
   L->ok = false;
   if (Cin < 1 || taps < 1 || pad > halo || pad < 0) return false;
   if ((taps - 1) * dil - pad > halo) return false;  // right halo
+  if (g_tc_split256 < 0) {
+    const char* e = getenv("DISSC_TC_SPLIT256");
+    g_tc_split256 = e ? (atoi(e) != 0) : 1;
+  }
   int NC;
+  if (force_nc == 0 && g_tc_split256 && ncols >= 256 && ncols % 256 == 0) force_nc = 128;
   if (force_nc) {
     if ((force_nc != 16 && force_nc != 32 && force_nc != 64 && force_nc != 128 && force_nc != 256) || ncols % force_nc)
       return false;
@@ -220,7 +229,7 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
   }
   if (g_single_acc256 < 0) {
     const char* e = getenv("DISSC_TC_SINGLE_ACC");
-    g_single_acc256 = e ? (atoi(e) != 0) : 1;
+    g_single_acc256 = e ? (atoi(e) != 0) : 0;
   }
   L->Cin = Cin; L->Cin_pad = (Cin + 15) / 16 * 16; L->NC = NC; L->n_chunks = ncols / NC;
   L->k = taps; L->dil = dil; L->pad = pad;
@@ -259,10 +268,13 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
     // taken when >= 4 weight slots remain (the ring only has to cover the L2 latency).  DISSC_TC_NA=2 restores two.
     if (g_tc_na_pref < 0) {
       const char* e = getenv("DISSC_TC_NA");
-      g_tc_na_pref = e ? atoi(e) : 2;
+      g_tc_na_pref = e ? atoi(e) : 0;   // 0: the heuristic below
     }
     L->split_w = g_tc_split_w;
-    for (int na = (NC >= 128) ? std::max(2, std::min(4, g_tc_na_pref)) : 2; na >= 2; --na) {
+    // measured (profiles/README.md, r02): with 8 channel blocks per item (Cin = 256) four activation buffers pay, with
+    // 4 (Cin = 128) they do not
+    const int na_pref = g_tc_na_pref > 0 ? g_tc_na_pref : (L->n_cb >= 8 ? 4 : 2);
+    for (int na = (NC >= 128) ? std::max(2, std::min(4, na_pref)) : 2; na >= 2; --na) {
       const size_t fixed = (size_t)na * a_bytes + misc(8);
       if (budget <= fixed + 2 * slot) continue;
       const int ns = (int)std::min<size_t>(8, (budget - fixed) / slot);
@@ -288,7 +300,8 @@ bool tc_plan_conv(int Cin, int Cout, int k, int dil, TcLayer* L) {
 static bool tc_plan_convt(int Cin, int Cout, int k, int u, TcLayer* L) {
   if (Cout % 8 || Cout > 256 || u < 1) return false;
   const int M = (k + u - 1) / u;
-  if (!tc_plan(Cin, u * Cout, M, 1, M - 1, L, kTcHalo)) return false;
+  // a chunk holds whole output phases (NC % Cout == 0): 256-channel upsamplers keep 256-column chunks
+  if (!tc_plan(Cin, u * Cout, M, 1, M - 1, L, kTcHalo, Cout == 256 ? 256 : 0)) return false;
   if (L->NC % Cout) { L->ok = false; return false; }
   L->Cout = Cout; L->up = u; L->up_P = L->NC / Cout; L->up_pad = (k - u) / 2;
   return true;
@@ -427,7 +440,8 @@ int launch_zero_halos(__half* hi, __half* lo, int slabs, int Tp, int T, cudaStre
 // fused ResBlock pair (resblock_tc.cuh): plan + launch
 // ------------------------------------------------------------------------
 constexpr int kPairHalo = 32;    // f32h: slack rows in front of every slab (>= p1 + p2 = 30 for k=11, d=5)
-constexpr int kPairSlack = 224;  // f32h: Tpf = roundup(T,128) + kPairSlack
+constexpr int kPairSlack = 352;  // f32h: Tpf = roundup(T,128) + kPairSlack (a 256-sample tile of the packed kernel reads
+                                 // up to ~256 + 30 rows past the last sample)
 static int g_use_pair = -1;      // DISSC_TC_PAIR=0 disables the fused pair kernel
 
 struct PairLayer {
@@ -483,6 +497,92 @@ static int launch_pair(PairParams p, const PairLayer& L, const TcLayer& c1, cons
   const int grid = std::min(p.n_tiles, num_sms() * L.ctas_per_sm);
   if (L.C == 16) return launch_pair_nc<16>(p, L, grid, st);
   return launch_pair_nc<32>(p, L, grid, st);
+}
+
+// ------------------------------------------------------------------------
+// fused ResBlock pair, C = 16, two samples per GEMM row (resblock_pack2_tc.cuh): plan + weights + launch
+// ------------------------------------------------------------------------
+static int g_use_pack2 = -1;  // DISSC_TC_PACK2=0 falls back to the one-sample-per-row pair kernel
+
+struct Pack2Layer {
+  bool ok = false;
+  int k = 0, dil = 1, S = 0, U = 0, M_out = 0;
+  int base[kPack2MaxDil] = {}, n_out[kPack2MaxDil] = {};
+  unsigned d_magic = 0;
+  size_t smem = 0;
+  __half* w1 = nullptr;  // block-Toeplitz packed weights (device)
+  __half* w2 = nullptr;
+  float inv1 = 1.f, inv2 = 1.f;
+};
+
+// Largest even U (xt samples per tile) whose d phases -- each ceil(n/2) rows of decimated sample pairs, inputs of a
+// phase directly followed by the next phase -- keep every OUTPUT row inside the 128 TMEM lanes and every input row
+// inside the 128 + S - 1 operand rows.
+static bool pack2_plan(int C, int k, int dil, Pack2Layer* L) {
+  L->ok = false;
+  if (g_use_pack2 < 0) {
+    const char* e = getenv("DISSC_TC_PACK2");
+    g_use_pack2 = e ? (atoi(e) != 0) : 1;
+  }
+  if (!g_use_pack2 || C != 16 || !(k & 1) || k < 1 || k > 33 || dil < 1 || dil > kPack2MaxDil) return false;
+  const int p1 = dil * (k - 1) / 2, p2 = (k - 1) / 2, S = (k + 1) / 2, RX = 128 + S - 1;
+  if (p1 + p2 > kPairHalo) return false;
+  for (int U = 256; U >= 64 + (k - 1); U -= 2) {
+    const int Lx = U + (k - 1) * dil;
+    int base = 0;
+    bool ok = true;
+    for (int f = 0; f < dil && ok; ++f) {
+      const int n_out = U > f ? (U - f + dil - 1) / dil : 0;
+      const int n_in = (Lx - f + dil - 1) / dil;
+      L->base[f] = base;
+      L->n_out[f] = n_out;
+      ok = base + (n_out + 1) / 2 <= 128 && base + (n_in + 1) / 2 <= RX;
+      base += (n_in + 1) / 2;
+    }
+    if (!ok) continue;
+    L->k = k; L->dil = dil; L->S = S; L->U = U; L->M_out = U - (k - 1);
+    L->d_magic = (unsigned)(0xFFFFFFFFu / (unsigned)dil + 1u);   // ceil(2^32 / d); d = 1: wraps to 0, handled below
+    const size_t stg = (size_t)2 * Lx * 32, tile = (size_t)2 * 4 * RX * 16, w = (size_t)S * 4096;
+    L->smem = 2 * stg + 4 * tile + 2 * w + 2 * 16 * 4 + 17 * 8 + 128;
+    if (L->smem > kSmemPerSm - 1536) return false;
+    L->ok = true;
+    return true;
+  }
+  return false;
+}
+
+// B_s[(qi, ci), (qo, co)] = W[co][ci][2s + qi - qo] (zero outside the kernel), packed like every other tensor-core weight
+// ([shift][k8][hi|lo][32][8], power-of-two pre-scale)
+static std::vector<__half> pack2_weights(const float* w, int k, int S, float* inv_scale) {
+  TcLayer V;
+  V.Cin = 32; V.Cin_pad = 32; V.NC = 32; V.n_chunks = 1; V.k = S; V.KB = 32; V.n_cb = 1;
+  return pack_weights_tc(V, [=](int n, int cip, int sh) {
+    const int qo = n >> 4, co = n & 15, qi = cip >> 4, ci = cip & 15, j = 2 * sh + qi - qo;
+    return (j >= 0 && j < k) ? w[((size_t)co * 16 + ci) * k + j] : 0.f;
+  }, inv_scale);
+}
+
+static int launch_pack2(Pack2Params p, const Pack2Layer& L, cudaStream_t st) {
+  static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
+  const int dev_ = current_device_slot();
+  if (!attr_set[dev_]) {
+    DISSC_CUDA(cudaFuncSetAttribute(resblock_pack2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSmemPerSm - 1024)));
+    attr_set[dev_] = true;
+  }
+  p.k = L.k; p.dil = L.dil; p.S = L.S; p.U = L.U; p.M_out = L.M_out;
+  for (int f = 0; f < kPack2MaxDil; ++f) { p.base[f] = L.base[f]; p.n_out[f] = L.n_out[f]; }
+  p.d_magic = L.d_magic;
+  if (p.in_scale == 0.f) p.in_scale = 1.f;
+  if (p.xt_scale == 0.f) p.xt_scale = 1.f;
+  if (p.plane_scale == 0.f) p.plane_scale = 1.f;
+  p.w1 = L.w1; p.w2 = L.w2; p.inv1 = L.inv1 / p.in_scale; p.inv2 = L.inv2 / p.xt_scale;
+  p.tiles_per_b = (p.T + L.M_out - 1) / L.M_out;
+  p.n_tiles = p.B * p.tiles_per_b;
+  const int grid = std::min(p.n_tiles, num_sms());
+  DISSC_CUDA(launch_pdl(resblock_pack2_tc_kernel, grid, kPack2Threads, L.smem, st, p));
+  DISSC_CUDA(cudaGetLastError());
+  return DISSC_OK;
 }
 
 // ------------------------------------------------------------------------
@@ -588,6 +688,7 @@ struct dissc_gen {
   bool stage_tc[DISSC_MAX_STAGES] = {};
   PairLayer rb_pair[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // fused (c1,c2) pairs, narrow stages
   bool stage_pair[DISSC_MAX_STAGES] = {};
+  dissc::Pack2Layer rb_pack2[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // C = 16 pairs, two samples per row
   dissc::Pair64Layer rb_pair64[DISSC_MAX_STAGES][DISSC_MAX_KERNELS][DISSC_MAX_DILATIONS];  // fused pairs of the C = 64 stage
   bool stage_pair64[DISSC_MAX_STAGES] = {};
   TcLayer pre_tc, ups_tc[DISSC_MAX_STAGES];  // conv_pre / upsamplers on the tensor cores
@@ -1030,6 +1131,20 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
               }
             }
           }
+          if (g->rb_pack2[i][j][m].ok) {   // C = 16: two samples per GEMM row (resblock_pack2_tc.cuh), same tensors
+            Pack2Params r{};
+            r.x = q.x; r.b1 = q.b1; r.b2 = q.b2; r.acc_in = q.acc_in; r.out_f = q.out_f; r.out_hi = q.out_hi;
+            r.out_lo = q.out_lo; r.out_plain = q.out_plain; r.lengths = q.lengths; r.len_mul = q.len_mul;
+            r.B = q.B; r.T = q.T; r.Tpf = q.Tpf; r.f_halo = q.f_halo; r.Tp = q.Tp; r.p_halo = q.p_halo;
+            r.in_scale = q.in_scale; r.xt_scale = q.xt_scale; r.plane_scale = q.plane_scale;
+            r.div = q.div; r.plane_act = q.plane_act; r.plain_act = q.plain_act; r.plane_slope = q.plane_slope;
+            r.plain_slope = q.plain_slope;
+            snprintf(name, sizeof(name), "s%d.rb%d.pair.%d.pk2", i, j, m);
+            DISSC_TRY(L.begin(name, 2 * fl, by1 + by2));
+            DISSC_TRY(launch_pack2(r, g->rb_pack2[i][j][m], st));
+            DISSC_TRY(L.end());
+            continue;
+          }
           snprintf(name, sizeof(name), "s%d.rb%d.pair.%d.ptc", i, j, m);
           DISSC_TRY(L.begin(name, 2 * fl, by1 + by2));
           DISSC_TRY(launch_pair(q, g->rb_pair[i][j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1], st));
@@ -1379,6 +1494,18 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
       for (int m = 0; m < c.n_dil && g->stage_pair[i]; ++m)
         g->stage_pair[i] = pair_plan(c.c0 >> (i + 1), c.rk[j], c.dil[j][m], g->rb_tc[i][j][m][0], g->rb_tc[i][j][m][1],
                                      &g->rb_pair[i][j][m]);
+    // C = 16: the same pairs with two samples per GEMM row (wider MMAs); per pair, falls back to the kernel above
+    if (g->stage_pair[i] && (c.c0 >> (i + 1)) == 16) {
+      for (int j = 0; j < c.n_rk; ++j)
+        for (int m = 0; m < c.n_dil; ++m) {
+          Pack2Layer& P = g->rb_pack2[i][j][m];
+          if (!pack2_plan(16, c.rk[j], c.dil[j][m], &P)) continue;
+          const std::string pfx = "resblocks." + std::to_string(i * c.n_rk + j);
+          auto k1 = pack2_weights(wm.get(pfx + ".convs1." + std::to_string(m) + ".weight")->data, P.k, P.S, &P.inv1);
+          auto k2 = pack2_weights(wm.get(pfx + ".convs2." + std::to_string(m) + ".weight")->data, P.k, P.S, &P.inv2);
+          if ((rc = tc_upload(g, k1, &P.w1)) || (rc = tc_upload(g, k2, &P.w2))) return fail(rc);
+        }
+    }
     // C = 64: planes-in / planes-out fused pairs with streamed weights (the stage after must not be the last one: its
     // output goes on as planes)
     g->stage_pair64[i] = g->tc_all && c.resblock == 1 && !g->stage_pair[i] && (c.c0 >> (i + 1)) == 64 && i + 1 < c.n_up;
@@ -1451,6 +1578,7 @@ int dissc_tc_set_tuning(int key, int value) {
   switch (key) {
     case 0: dissc::g_tc_na_pref = value; return DISSC_OK;
     case 1: dissc::g_tc_split_w = value ? 1 : 0; return DISSC_OK;
+    case 2: dissc::g_tc_split256 = value ? 1 : 0; return DISSC_OK;
   }
   return dissc::set_err(DISSC_EINVAL, "unknown tuning key %d", key);
 }
@@ -1926,7 +2054,27 @@ int dissc_resblock_pair_tc(const float* in, const float* w1_host, const float* b
   p.B = B; p.T = T; p.Tpf = Tpf; p.f_halo = kPairHalo; p.Tp = Tp; p.p_halo = kTcHalo;
   p.div = div; p.plane_act = 1; p.plane_slope = plane_slope;
   p.in_scale = s_in; p.xt_scale = s_xt; p.plane_scale = s_out;
-  if (!rc) rc = launch_pair(p, L, c1, c2, st);
+  Pack2Layer P2;
+  if (!rc && pack2_plan(C, k, dilation, &P2)) {   // C = 16: the two-samples-per-row kernel is the one the model runs
+    auto q1 = pack2_weights(w1_host, k, P2.S, &P2.inv1), q2 = pack2_weights(w2_host, k, P2.S, &P2.inv2);
+    P2.w1 = (__half*)dalloc(q1.size() * 2);
+    P2.w2 = (__half*)dalloc(q2.size() * 2);
+    if (!P2.w1 || !P2.w2) {
+      cleanup();
+      return set_err(DISSC_ENOMEM, "cudaMalloc failed in dissc_resblock_pair_tc");
+    }
+    cudaMemcpyAsync(P2.w1, q1.data(), q1.size() * 2, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(P2.w2, q2.data(), q2.size() * 2, cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);   // q1 / q2 are about to go out of scope
+    Pack2Params r{};
+    r.x = p.x; r.b1 = p.b1; r.b2 = p.b2; r.acc_in = p.acc_in; r.out_f = p.out_f; r.out_hi = p.out_hi; r.out_lo = p.out_lo;
+    r.lengths = p.lengths; r.len_mul = p.len_mul; r.B = p.B; r.T = p.T; r.Tpf = p.Tpf; r.f_halo = p.f_halo; r.Tp = p.Tp;
+    r.p_halo = p.p_halo; r.in_scale = s_in; r.xt_scale = s_xt; r.plane_scale = s_out; r.div = div; r.plane_act = 1;
+    r.plane_slope = plane_slope;
+    rc = launch_pack2(r, P2, st);
+  } else if (!rc) {
+    rc = launch_pair(p, L, c1, c2, st);
+  }
   if (!rc && out_raw) tc_f32b_to_plain_kernel<<<nb, 256, 0, st>>>(f_out + (size_t)kPairHalo * 8, out_raw, B, C, T, Tpf);
   if (!rc && out_planes) tc_planes_to_plain_kernel<<<nb, 256, 0, st>>>(o_hi, o_lo, out_planes, B, C, T, Tp, 1.f / s_out);
   cudaError_t e = cudaStreamSynchronize(st);

@@ -183,14 +183,16 @@ class CodeGenerator(nn.Module):
             lengths = lengths.to(device=code.device, dtype=torch.int32).contiguous()
         return self._run(code, f0, spkr, lengths, B, T, out_dtype=torch.float32).view(B, 1, -1)
 
-    def generate_int16(self, code, f0=None, spkr=None, lengths=None):
-        """Fused ``generate()`` of sr/inference.py:67-76: returns int16 (B, hop*T) on the device."""
+    def generate_int16(self, code, f0=None, spkr=None, lengths=None, out=None):
+        """Fused ``generate()`` of sr/inference.py:67-76: returns int16 (B, hop*T) on the device.  ``out``: an existing
+        contiguous int16 (B, hop*T) device tensor the last kernel writes into directly (e.g. the send buffer of a
+        gather, ``dist.ScatterGatherPipeline``)."""
         B, T = code.shape
         f0 = None if f0 is None else f0.reshape(B, T).to(torch.float32).contiguous()
         spkr = None if spkr is None else spkr.reshape(B).to(torch.int64).contiguous()
         if lengths is not None:
             lengths = lengths.to(device=code.device, dtype=torch.int32).contiguous()
-        return self._run(code.contiguous(), f0, spkr, lengths, B, T, out_dtype=torch.int16)
+        return self._run(code.contiguous(), f0, spkr, lengths, B, T, out_dtype=torch.int16, out=out)
 
     # ---- C-ABI plumbing ------------------------------------------------------
     def folded_state_dict(self):
@@ -274,7 +276,7 @@ class CodeGenerator(nn.Module):
         _lib.check(_lib.lib().dissc_gen_workspace_bytes(self._ensure_handle(device), B, T, ctypes.byref(n)))
         return n.value
 
-    def _run(self, code, f0, spkr, lengths, B, T, out_dtype, ws=None):
+    def _run(self, code, f0, spkr, lengths, B, T, out_dtype, ws=None, out=None):
         dev = code.device
         L = _lib.lib()
         h = self._ensure_handle(dev)
@@ -287,7 +289,10 @@ class CodeGenerator(nn.Module):
         t_out = T
         for u, k in zip(self.rates, self.up_kernels):
             t_out = (t_out - 1) * u - 2 * ((k - u) // 2) + k
-        out = torch.empty((B, t_out), dtype=out_dtype, device=dev)
+        if out is None:
+            out = torch.empty((B, t_out), dtype=out_dtype, device=dev)
+        elif out.dtype != out_dtype or out.numel() != B * t_out or not out.is_contiguous() or out.device != dev:
+            raise ValueError(f"out must be a contiguous {out_dtype} tensor of {B * t_out} elements on {dev}")
         ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -325,17 +330,37 @@ class CodeGenerator(nn.Module):
 
     def forward_host(self, code, f0, spkr, lengths=None, out=None, int16=False, device=0):
         """End-to-end C-ABI call with HOST (ideally pinned) tensors: H2D + forward + D2H + sync."""
+        out = self.forward_host_submit(0, code, f0, spkr, lengths=lengths, out=out, int16=int16, device=device)
+        self.forward_host_wait(0)
+        return out
+
+    def forward_host_submit(self, slot, code, f0, spkr, lengths=None, out=None, int16=False, device=0):
+        """Pipelined host entry (``dissc_gen_forward_host_submit``): enqueue H2D -> forward -> D2H for ``slot`` (0 or 1)
+        and return the host output tensor WITHOUT waiting; it is valid after ``forward_host_wait(slot)``.  Submitting
+        the other slot before waiting hides one batch's copy-back under the next batch's forward.  The host tensors
+        of a slot must stay alive (and should be pinned) until its wait returns."""
         B, T = code.shape
         dev = torch.device("cuda", device)
         h = self._ensure_handle(dev)
         if out is None:
-            t_out = self.hop * T
-            out = torch.empty((B, t_out), dtype=torch.int16 if int16 else torch.float32).pin_memory()
+            out = torch.empty((B, self.hop * T), dtype=torch.int16 if int16 else torch.float32).pin_memory()
         ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
-        _lib.check(_lib.lib().dissc_gen_forward_host(
-            h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T,
-            None if int16 else ptr(out), ptr(out) if int16 else None), "dissc_gen_forward_host")
+        self.__dict__.setdefault("_host_keep", {})[slot] = (code, f0, spkr, lengths, out)
+        _lib.check(_lib.lib().dissc_gen_forward_host_submit(
+            h, slot, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T,
+            None if int16 else ptr(out), ptr(out) if int16 else None), "dissc_gen_forward_host_submit")
         return out
+
+    def forward_host_wait(self, slot):
+        if self._handle is None:
+            return
+        _lib.check(_lib.lib().dissc_gen_forward_host_wait(self._handle, slot), "dissc_gen_forward_host_wait")
+        self.__dict__.get("_host_keep", {}).pop(slot, None)
+
+    def host_reserve(self, B, T, device=0):
+        """Pre-size the device staging arena of the host entry points for (B, T) batches."""
+        _lib.check(_lib.lib().dissc_gen_host_reserve(self._ensure_handle(torch.device("cuda", device)), B, T),
+                   "dissc_gen_host_reserve")
 
     def check_indices(self, synchronize=True):
         """Raises ``IndexError`` if a unit / speaker id outside its embedding table reached the kernels since the last

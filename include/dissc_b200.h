@@ -148,14 +148,18 @@ int dissc_gen_status(dissc_gen_t* g);
 int dissc_gen_set_tensor_cores(dissc_gen_t* g, int enable);
 int dissc_gen_tensor_core_stages(const dissc_gen_t* g); /* how many stages currently take the tensor-core path */
 
-/* N=256 tensor-core layers: 1 (default) = the three split-precision MMAs share ONE TMEM accumulator, which leaves
- * room to double-buffer tiles (stage 0 runs 23 % faster; waveform error 1.8e-5 max-abs vs fp64); 0 = separate main and
- * cross-term accumulators (7e-6).  Applies to handles / layer calls created afterwards.  Returns the previous setting
- * (-1 = never set: env DISSC_TC_SINGLE_ACC or the default decides). */
+/* 256-column GEMMs (the C = 256 stage, conv_pre, the first upsampler).  Default: two 128-column chunks, each with
+ * separate main and cross-term accumulators double-buffered in TMEM (waveform error 7e-6 max-abs vs fp64 on the benchmark
+ * weights, 4e-5 on the `hot` recipe).  Opt-in fast mode: dissc_tc_set_tuning(2, 0) + dissc_tc_set_single_accumulator(1) =
+ * one 256-column chunk with all three split-precision MMAs into ONE accumulator (stage 0 10 % faster; the tensor core
+ * truncates the accumulator after every MMA, so the error is 2.5x larger: 1.8e-5 / 1.0e-4).  Both apply to handles /
+ * layer calls created afterwards.  dissc_tc_set_single_accumulator returns the previous setting (-1 = never set: env
+ * DISSC_TC_SINGLE_ACC or the default 0 decides). */
 int dissc_tc_set_single_accumulator(int enable);
 /* Plan-time tuning of the tensor-core conv kernel, read when a handle is created (A/B measurements, scripts/ab_tuning.py):
- * key 0 = preferred number of activation buffers of the streamed-weight layers (2..4), key 1 = separate weight-producer
- * thread in the N >= 128 kernels (0 / 1).  No reference counterpart. */
+ * key 0 = number of activation buffers of the streamed-weight layers (2..4; 0 = heuristic), key 1 = separate
+ * weight-producer thread in the N >= 128 kernels (0 / 1), key 2 = 256-column GEMMs as two 128-column chunks (1, default)
+ * or one 256-column chunk (0).  No reference counterpart. */
 int dissc_tc_set_tuning(int key, int value);
 
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */

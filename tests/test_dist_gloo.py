@@ -55,6 +55,40 @@ def _worker(rank, world, port, ret):
         ret.put("ok")
     else:
         assert g16 is None
+    # overlapped pipeline (one packed scatter, double-buffered gather): 5 steps through 2 buffers, every step's gathered
+    # result must be that step's inputs routed to the right rank and back
+    hop = 4
+
+    def fake_forward(c_, f_, s_, l_, out):   # "waveform" = f(code, f0 sign, spkr, lengths, rank)
+        base = (c_.sum(1) + s_ + l_.to(torch.int64) + (f_ > 0).sum(1) + 1000 * rank).to(torch.int16)
+        out.copy_(base.view(-1, 1).expand(-1, hop * T) + torch.arange(hop * T, dtype=torch.int16))
+
+    pipe = ddist.ScatterGatherPipeline(rank, world, dev, B_local, T, hop, fake_forward)
+    for step in range(5):
+        if rank == 0:
+            gs = torch.Generator().manual_seed(100 + step)
+            code_s = torch.randint(0, 100, (world * B_local, T), generator=gs)
+            f0_s = torch.randn(world * B_local, T, generator=gs)
+            spkr_s = torch.randint(0, 50, (world * B_local,), generator=gs)
+            len_s = torch.randint(1, T + 1, (world * B_local,), generator=gs, dtype=torch.int32)
+            packed = ddist.pack_inputs(code_s, f0_s, spkr_s, len_s, world)
+            assert packed.shape == (world, ddist.packed_layout(B_local, T)[1])
+            c0, f0_0, s0, l0 = ddist.unpack_inputs(packed[1], B_local, T)      # round trip of rank 1's row
+            assert torch.equal(c0, code_s[B_local:2 * B_local]) and torch.equal(f0_0, f0_s[B_local:2 * B_local])
+            assert torch.equal(s0, spkr_s[B_local:2 * B_local]) and torch.equal(l0, len_s[B_local:2 * B_local])
+        else:
+            packed = None
+        i = pipe.step(packed)
+        pipe.wait(i)
+        if rank == 0:
+            got = pipe.gathered[i]
+            assert got.shape == (world, B_local, hop * T) and got.dtype == torch.int16
+            for r in range(world):
+                sl = slice(r * B_local, (r + 1) * B_local)
+                base = (code_s[sl].sum(1) + spkr_s[sl] + len_s[sl].to(torch.int64) + (f0_s[sl] > 0).sum(1) + 1000 * r)
+                want = base.to(torch.int16).view(-1, 1) + torch.arange(hop * T, dtype=torch.int16)
+                assert torch.equal(got[r], want), (step, r)
+    pipe.flush()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,6 +104,23 @@ def test_scatter_gather_world2():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == "ok"
+
+
+def test_pipeline_single_rank_is_identity():
+    """world == 1: no collective, the forward writes the result buffer itself."""
+    from dissc_b200 import dist as ddist
+    B, T, hop = 2, 3, 2
+    code = torch.arange(B * T).reshape(B, T)
+    packed = ddist.pack_inputs(code, torch.ones(B, T), torch.tensor([5, 6]), torch.tensor([3, 2], dtype=torch.int32), 1)
+
+    def fwd(c, f, s, l, out):
+        out.copy_((c.sum(1) + s).to(torch.int16).view(-1, 1).expand(-1, hop * T))
+
+    pipe = ddist.ScatterGatherPipeline(0, 1, torch.device("cpu"), B, T, hop, fwd)
+    i = pipe.step(packed)
+    pipe.wait(i)
+    assert pipe.gathered[i].shape == (1, B, hop * T)
+    assert pipe.gathered[i][0, :, 0].tolist() == [0 + 1 + 2 + 5, 3 + 4 + 5 + 6]
 
 
 def test_pack_batch_pads_and_records_lengths():

@@ -147,6 +147,52 @@ def test_int16_and_host_entry(cuda_device, vctk_gen):
     assert np.array_equal(ih.numpy(), want)
 
 
+def test_pipelined_host_entry(cuda_device, vctk_gen):
+    """dissc_gen_forward_host_submit / _wait: two batches in flight, every output equals the synchronous call."""
+    gen, _ = vctk_gen
+    batches = []
+    for seed in (21, 22, 23, 24, 25):
+        code, f0, spkr = syn.synthetic_inputs(2, 30 + seed, seed=seed)
+        batches.append((code.pin_memory(), f0.reshape(2, -1).contiguous().pin_memory(),
+                        spkr.reshape(2).contiguous().pin_memory()))
+    want = [gen.forward_host(*b, int16=True).clone() for b in batches]
+    gen.host_reserve(2, 64)
+    outs = [None] * len(batches)
+    for i, b in enumerate(batches):
+        outs[i] = gen.forward_host_submit(i % 2, *b, int16=True)
+        if i > 0:
+            gen.forward_host_wait((i - 1) % 2)
+            assert torch.equal(outs[i - 1], want[i - 1]), i - 1
+    gen.forward_host_wait((len(batches) - 1) % 2)
+    assert torch.equal(outs[-1], want[-1])
+    with pytest.raises(Exception):
+        gen.forward_host_submit(2, *batches[0])   # only two slots
+
+
+def test_scatter_gather_pipeline_single_gpu(cuda_device, vctk_gen):
+    """dist.ScatterGatherPipeline at world = 1 (no collective): the packed inputs come back as the int16 forward of the
+    same inputs, for every step through both buffers; the last kernel writes the result buffer directly."""
+    from dissc_b200 import dist as ddist
+    gen, _ = vctk_gen
+    B, T = 3, 40
+    pipe = ddist.ScatterGatherPipeline(0, 1, cuda_device, B, T, gen.hop,
+                                       lambda c, f, s, l, out: gen.generate_int16(c, f, s, lengths=l, out=out))
+    for step in range(4):
+        code, f0, spkr = syn.synthetic_inputs(B, T, seed=50 + step)
+        lengths = torch.tensor([T, T - 7, 1], dtype=torch.int32)
+        packed = ddist.pack_inputs(code.to(cuda_device), f0.reshape(B, T).to(cuda_device), spkr.reshape(B).to(cuda_device),
+                                   lengths.to(cuda_device), 1)
+        i = pipe.step(packed)
+        pipe.wait(i)
+        want = gen.generate_int16(code.to(cuda_device), f0.to(cuda_device), spkr.to(cuda_device),
+                                  lengths=lengths.to(cuda_device))
+        torch.cuda.synchronize()
+        assert torch.equal(pipe.gathered[i][0], want), step
+    with pytest.raises(ValueError):
+        gen.generate_int16(code.to(cuda_device), f0.to(cuda_device), spkr.to(cuda_device),
+                           out=torch.empty((B, 5), dtype=torch.int16, device=cuda_device))
+
+
 def test_deterministic_and_batch_invariant(cuda_device, vctk_gen):
     gen, _ = vctk_gen
     code, f0, spkr = syn.synthetic_inputs(4, 40, seed=8)
@@ -249,4 +295,4 @@ def test_tuning_knobs_do_not_change_results(cuda_device, vctk_gen):
         assert L.dissc_tc_set_tuning(99, 0) != 0   # unknown key: error code, message in dissc_last_error()
     finally:
         L.dissc_tc_set_tuning(1, 1)
-        L.dissc_tc_set_tuning(0, 2)
+        L.dissc_tc_set_tuning(0, 0)   # 0 = the planner's own choice

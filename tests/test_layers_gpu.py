@@ -157,7 +157,10 @@ def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0,
     """xscale multiplies every activation-like input (x, bias, residual, accumulator): the op is positively homogeneous,
     so the expected output scales by the same factor and the tolerance is relative to it."""
     from dissc_b200 import _lib
+    # opt-in fast mode for 256-column GEMMs: one 256-column chunk, all three MMAs into ONE accumulator (the default is
+    # two 128-column chunks with separate main / cross accumulators)
     _lib.lib().dissc_tc_set_single_accumulator(int(single_acc))
+    _lib.lib().dissc_tc_set_tuning(2, 0 if single_acc else 1)
     g = torch.Generator().manual_seed(seed)
     Cin = Cin or C
     x = xscale * torch.randn(B, Cin, T, generator=g)
@@ -194,7 +197,8 @@ def _tc_case(dev, B, C, T, k, d, pre, post, res, acc, div, lengths=None, seed=0,
                                                int(post), 0.01, float(div), None))
     torch.cuda.synchronize()
     scale = max(1.0, wscale) * xscale
-    _lib.lib().dissc_tc_set_single_accumulator(1)  # library default
+    _lib.lib().dissc_tc_set_single_accumulator(0)  # library defaults
+    _lib.lib().dissc_tc_set_tuning(2, 1)
     for name, got, want in (("plain", outs[0].cpu(), y), ("raw", outs[1].cpu(), raw), ("planes", outs[2].cpu(), y)):
         got = got.clone()
         want = want.clone()
@@ -218,10 +222,12 @@ def test_tc_conv_resblock_shapes(cuda_device, C, k, d):
 
 @pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
 def test_tc_conv_single_accumulator_n256(cuda_device, k, d):
-    # N=256 default mode: all three split-precision MMAs into ONE TMEM accumulator (the tensor core truncates the
-    # accumulator after every MMA, so the error grows with Cin*k/16 steps) -- looser per-layer tolerance, still
-    # 1.8e-5 max-abs on the end-to-end waveform (scripts/parity_report.py).
+    # N=256 OPT-IN fast mode: all three split-precision MMAs into ONE TMEM accumulator (the tensor core truncates the
+    # accumulator after every MMA, so the error grows with 3 * Cin*k/16 accumulations) -- looser per-layer tolerance; end
+    # to end it costs 2.5x the waveform error (1.0e-4 instead of 4e-5 on the `hot` weights), which is why it is not the
+    # default.  The default (two 128-column chunks, dual accumulators) holds the tight tolerance:
     _tc_case(cuda_device, 2, 256, 300, k, d, pre=True, post=True, res=True, acc=False, div=0, tol=1e-4, single_acc=True)
+    _tc_case(cuda_device, 2, 256, 300, k, d, pre=True, post=True, res=True, acc=False, div=0)
 
 
 def test_tc_conv_epilogue_modes(cuda_device):
@@ -260,6 +266,7 @@ def test_tc_conv_weight_scaling(cuda_device, wscale):
 @pytest.mark.parametrize("xscale", [1e-4, 1e-2, 1.0, 1e2, 1e3, 3e4])
 def test_tc_conv_activation_scale_sweep(cuda_device, xscale):
     _tc_case(cuda_device, 2, 64, 515, 7, 3, pre=True, post=True, res=True, acc=True, div=3.0, xscale=xscale)
+    _tc_case(cuda_device, 1, 256, 300, 11, 1, pre=True, post=True, res=True, acc=False, div=0, xscale=xscale)
     _tc_case(cuda_device, 1, 256, 300, 11, 1, pre=True, post=True, res=True, acc=False, div=0, xscale=xscale, tol=1e-4,
              single_acc=True)
     _tc_case(cuda_device, 2, 16, 2500, 3, 1, pre=True, post=False, res=False, acc=False, div=0, xscale=xscale)
@@ -296,7 +303,6 @@ def _tc_convt_case(dev, B, Cin, Cout, k, u, T, lengths=None, seed=0):
         _lib.check(_lib.lib().dissc_conv_transpose1d_tc(_ptr(xd), _ptr(w), _ptr(b), _ptr(raw), _ptr(pl), _ptr(ld), 1,
                                                          B, Cin, Cout, T, k, u, 0.1, None))
     torch.cuda.synchronize()
-    _lib.lib().dissc_tc_set_single_accumulator(1)  # library default
     raw, pl = raw.cpu(), pl.cpu()
     wantp = F.leaky_relu(want, 0.1)
     if lengths is not None:

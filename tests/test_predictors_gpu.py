@@ -145,3 +145,39 @@ def test_pitch_new_rejects_more_than_850_units(cuda_device):
     seq = torch.zeros((1, 851), dtype=torch.int64, device=cuda_device)
     with pytest.raises(_lib.DisscError):
         pn(seq, torch.zeros((1, 1), dtype=torch.int64, device=cuda_device))
+
+
+def test_out_of_range_ids_raise(cuda_device):
+    """nn.Embedding raises IndexError on a token / speaker id outside its table (model/len_predictor.py:15-16,
+    model/pitch_predictor.py:51-52); here the gather stays in bounds and the error surfaces at check_indices()."""
+    from dissc_b200 import synthetic as syn
+    from dissc_b200.predictors import LenPredictor, PitchPredictor
+    lm = LenPredictor(100, 108).to(cuda_device)
+    lm.load_state_dict(syn.synthetic_len_predictor_state_dict(100, 108, seed=1))
+    mean, std = syn.synthetic_pitch_stats(108, seed=2)
+    pm = PitchPredictor(100, 108, id2pitch_mean=mean.to(cuda_device), id2pitch_std=std.to(cuda_device)).to(cuda_device)
+    pm.load_state_dict(syn.synthetic_pitch_predictor_state_dict("new", 100, 108, seed=3))
+    seq = torch.randint(0, 100, (2, 12), device=cuda_device)
+    spk = torch.tensor([[3], [7]], device=cuda_device)
+    lm(seq, spk)
+    lm.check_indices()
+    bad = seq.clone()
+    bad[1, 4] = 101                                  # table has n_tokens + 1 = 101 rows
+    out = lm(bad, spk)
+    assert torch.isfinite(out).all()
+    with pytest.raises(IndexError, match="unit"):
+        lm.check_indices()
+    lm(seq, torch.tensor([[3], [108]], device=cuda_device))   # LenPredictor's speaker table has exactly n_speakers rows
+    with pytest.raises(IndexError, match="speaker"):
+        lm.check_indices()
+    pm(seq, spk)
+    pm.check_indices()
+    pm(seq, torch.tensor([[-1], [7]], device=cuda_device))
+    with pytest.raises(IndexError, match="speaker"):
+        pm.check_indices()
+    # calc_freq with a speaker id outside the statistics tables: that row is NaN, the others are untouched
+    cls, reg = pm(seq, spk)
+    pm.check_indices()
+    good = pm.calc_freq(cls, reg, spk, norm=False)
+    odd = pm.calc_freq(cls, reg, torch.tensor([[3], [108]], device=cuda_device), norm=False)
+    assert torch.equal(odd[0], good[0]) and torch.isnan(odd[1]).all()
