@@ -72,7 +72,12 @@ def encode_files(encoder: SpeechEncoder, base_dir: str, files: Sequence[str], ou
 
 
 def build_parser():
-    ap = argparse.ArgumentParser()
+    ap = argparse.ArgumentParser(
+        description="HuBERT-base layer-6 + k-means units for every wav under --base_dir (data/encode.py).  NOTE: the "
+                    "reference also writes a YAAPT 'f0' per clip (CPU DSP inside textless, data/encode.py:32-38); that is "
+                    "not ported, so these manifests carry 'units' / 'durations' / 'audio' only.  Vocoder configs with "
+                    "\"f0\": true need an F0 contour: predict it with `python -m dissc_b200.infer --pred_pitch ...`, or "
+                    "merge an externally computed 50 Hz F0 track into the manifest (INTEGRATION.md section 3).")
     ap.add_argument("--model_name", default="hubert-base-ls960")
     ap.add_argument("--quantizer_name", default="kmeans")
     ap.add_argument("--vocab_size", default=100, type=int)

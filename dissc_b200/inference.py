@@ -284,6 +284,30 @@ def sample_df_targets(df, out_name: str, spkr_to_id: dict) -> List[int]:
     return [spkr_to_id[i] for i in df[df.syn_sample == cur_name].syn_trgt.unique()]
 
 
+def select_items(n_items: int, n: int, debug: bool) -> List[int]:
+    """Which manifest entries get processed, and in which order (sr/inference.py:340-359).
+
+    * ``--debug``: manifest order; the loop breaks once ``i > n``, i.e. entries ``0 .. n+1`` (n + 2 of them).
+    * otherwise: ``random.shuffle`` of all indices, then ``n + 1`` results are awaited from ``pool.imap`` (its counter
+      starts at 1).  ``main`` seeds the global RNG with 52 (:283-286) but ``CodeDataset.__init__`` re-seeds it with 1234
+      (sr/dataset.py:157) before the shuffle (:351), so the permutation is that of ``random.Random(1234)``.
+      (The reference's pool keeps working on a few more entries in the background until it is torn down; which extra
+      files appear is a race there and is not reproduced.)"""
+    idx = list(range(n_items))
+    if debug:
+        return idx if n == -1 else idx[: n + 2]
+    random.Random(1234).shuffle(idx)
+    return idx if n == -1 else idx[: n + 1]
+
+
+def vc_targets_for_item(item_index: int, n_speakers: int) -> List[int]:
+    """``--vc`` without ``--target-speakers``: five random target speakers PER UTTERANCE (sr/inference.py:210-211).
+    The reference draws them from its worker's RNG stream (seed 52 + GPU ordinal, :165-169), so which speakers an
+    utterance gets depends on how the pool happened to schedule it; here the draw is seeded by the utterance's
+    manifest index alone, hence reproducible and independent of rank / world size."""
+    return random.Random(52 * 1000003 + item_index).sample(range(n_speakers), k=min(5, n_speakers))
+
+
 def build_parser():
     """sr/inference.py:263-281."""
     ap = argparse.ArgumentParser()
@@ -364,8 +388,11 @@ def main(argv: Optional[Sequence[str]] = None):
                 f0_stats = pickle.load(f)
         items = prepare_items(h, audio_files, codes, pitch, id_to_spkr, f0_stats, a.unseen_speaker)
         gt_paths = list(audio_files)
-    items = items[: a.n + 1] if a.n != -1 else items           # reference stops after i > n (sr/inference.py:356-358)
-    gt_paths = gt_paths[: len(items)]
+    chosen = select_items(len(items), a.n, a.debug)            # sr/inference.py:340-359 (seeded shuffle, -n)
+    for pos, it in enumerate(items):
+        it["manifest_index"] = pos
+    items = [items[i] for i in chosen]
+    gt_paths = [gt_paths[i] for i in chosen]
     mine = ddist.shard_by_length([len(it["code"]) for it in items], world)[rank]
     my_items = [items[i] for i in mine]
     my_gt = [gt_paths[i] for i in mine]
@@ -399,10 +426,9 @@ def main(argv: Optional[Sequence[str]] = None):
     if h.get("multispkr", None) and a.vc:                      # voice conversion (sr/inference.py:209-251)
         if a.target_speakers is not None:
             spkrs = [spkr_to_id[s] for s in a.target_speakers]
+            per_item = [list(spkrs)] * len(my_items)
         else:
-            random.seed(52 + rank)
-            spkrs = random.sample(range(len(id_to_spkr)), k=min(5, len(id_to_spkr)))
-        per_item = [list(spkrs)] * len(my_items)
+            per_item = [vc_targets_for_item(it["manifest_index"], len(id_to_spkr)) for it in my_items]
         if df is not None:
             per_item = [sample_df_targets(df, out_name(it), spkr_to_id) for it in my_items]
         f0_tgt = None

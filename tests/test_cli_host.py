@@ -142,3 +142,23 @@ def test_wav_writer_background_threads(tmp_path):
     bad.submit(str(tmp_path / "no_such_dir" / "x.wav"), 16000, np.zeros(4, np.int16))
     with pytest.raises(OSError):
         bad.close()
+
+
+def test_select_items_follows_reference_shuffle_and_n():
+    """sr/inference.py:340-359: --debug walks the manifest until i > n (n + 2 entries); the pool path shuffles with the
+    RNG state CodeDataset.__init__ leaves behind (random.seed(1234), sr/dataset.py:157) and awaits n + 1 results."""
+    import random
+    from dissc_b200.inference import select_items, vc_targets_for_item
+    assert select_items(10, 3, debug=True) == [0, 1, 2, 3, 4]
+    assert select_items(3, 7, debug=True) == [0, 1, 2]
+    assert select_items(4, -1, debug=True) == [0, 1, 2, 3]
+    random.seed(1234)                      # what the reference's global RNG holds when main() shuffles
+    want = list(range(50))
+    random.shuffle(want)
+    assert select_items(50, -1, debug=False) == want
+    assert select_items(50, 9, debug=False) == want[:10]
+    # VC targets: five distinct speakers per utterance, a function of the manifest index only
+    a, b = vc_targets_for_item(7, 108), vc_targets_for_item(7, 108)
+    assert a == b and len(set(a)) == 5 and all(0 <= k < 108 for k in a)
+    assert vc_targets_for_item(8, 108) != a
+    assert len(vc_targets_for_item(0, 3)) == 3

@@ -106,3 +106,40 @@ def test_checkpoint_loaders_on_lookalikes(tmp_path, ta_model):
         pickle.dump(km, f)
     c = ck.load_kmeans_centers(str(tmp_path / "km.bin"))
     assert c.dtype == torch.float32 and c.shape == (3, 4) and c[2, 3] == 11
+
+
+def test_real_joblib_kmeans_dump_and_hostile_pickles(tmp_path):
+    """km.bin as the GSLM release ships it: joblib.dump of a fitted sklearn MiniBatchKMeans -- loaded here WITHOUT
+    instantiating any sklearn class; and pickles that try to call into os / builtins are defused, not executed."""
+    import pickle
+    joblib = pytest.importorskip("joblib")
+    cluster = pytest.importorskip("sklearn.cluster")
+    from dissc_b200 import checkpoints as ck
+    rng = np.random.RandomState(0)
+    km = cluster.MiniBatchKMeans(n_clusters=7, n_init=1, random_state=0, batch_size=64).fit(rng.randn(300, 12))
+    for name, kw in (("km.bin", {}), ("km_z.bin", {"compress": 3})):
+        joblib.dump(km, tmp_path / name, **kw)
+        c = ck.load_kmeans_centers(str(tmp_path / name))
+        assert c.dtype == torch.float32 and c.shape == (7, 12)
+        assert np.allclose(c.numpy(), km.cluster_centers_.astype(np.float32))
+
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, (f"touch {marker}",))
+
+    for payload, found in ((Evil(), False), ({"cluster_centers_": np.ones((2, 3)), "cfg": Evil()}, True)):
+        with open(tmp_path / "evil.bin", "wb") as f:
+            pickle.dump(payload, f)
+        try:
+            c = ck.load_kmeans_centers(str(tmp_path / "evil.bin"))
+            assert found and c.shape == (2, 3)
+        except ValueError:
+            assert not found                       # "no cluster_centers_ found"
+        assert not marker.exists()
+    torch.save({"model": {"w": torch.ones(2)}, "cfg": Evil()}, tmp_path / "evil.pt")
+    got = ck.load_fairseq_hubert(str(tmp_path / "evil.pt"))
+    assert not marker.exists() and torch.equal(got["w"], torch.ones(2))
+    assert ("builtins", "eval") not in ck._ALLOWED_GLOBALS and ("os", "system") not in ck._ALLOWED_GLOBALS
