@@ -74,6 +74,27 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
+// ---- thread-block clusters (2 CTAs sharing one weight stream, conv_tc.cuh) ----------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (also orders shared-memory / mbarrier initialisation before remote accesses)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 1-D bulk TMA delivered to the SAME shared-memory offset (data and mbarrier) of every CTA in `cta_mask`: one L2 read
+// feeds all of them.
+__device__ __forceinline__ void tma_load_1d_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
 // One lane of a CONVERGED warp (elect.sync).  Single-thread regions that issue tcgen05.mma / tcgen05.commit / bulk TMA
 // must be entered through this and not through `lane == 0`: the compiler then knows exactly one thread runs the region
 // and emits the uniform-datapath instructions (UTCHMMA, UTCBAR, UBLKCP) back to back; behind a plain divergent branch

@@ -93,6 +93,12 @@ struct TcParams {
   // would otherwise underflow / saturate).  The INPUT planes hold value * in_scale: the host folds 1 / in_scale into
   // w_inv_scale.  The OUTPUT planes are written as act(value) * plane_scale.  0 means 1.
   float in_scale, plane_scale;
+  int exp_half_w;        // EXPERIMENT ONLY (DISSC_EXP_HALFW=1, wrong results): stream half of every weight stage's bytes
+  // 2-CTA clusters sharing ONE weight stream (EPW == 8, streamed weights): the two CTAs of a cluster work on two
+  // different tiles of the same N chunk in lockstep; each loads half of every weight stage and multicasts it into both
+  // CTAs' shared memory, which halves the L2 -> SM weight traffic (43 B/clk/SM without it, the chip's L2 limit).
+  int cluster2;
+  int n_tiles;           // B * tiles_per_b
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -122,6 +128,15 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// commit that arrives on the mbarrier at the same offset in every CTA of `cta_mask` (a weight slot shared by a CTA pair
+// is free once BOTH CTAs' MMAs have read it)
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
                : "memory");
 }
 
@@ -250,6 +265,18 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // cluster mode: the pair (2i, 2i+1) walks "pair items" (chunk, tile pair) together; member r takes tile 2*pair + r.  An
+  // odd tile count makes the last pair compute its last tile twice (identical stores) so both keep the same weight sequence.
+  const bool cl2 = (PW == 3) && p.cluster2;
+  const uint32_t crank = cl2 ? cluster_ctarank() : 0;
+  const int it_first = cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int it_step = cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int it_count = cl2 ? ((p.n_tiles + 1) >> 1) * p.n_chunks : p.n_items;
+  auto item_of = [&](int it, int& chunk, int& tile) {
+    const int q = it / p.n_chunks;
+    chunk = it - q * p.n_chunks;
+    tile = cl2 ? min(2 * q + (int)crank, p.n_tiles - 1) : q;
+  };
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
     }
     for (int i = 0; i < p.NS; ++i) {
       mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
+      mbar_init(&w_empty[i], cl2 ? 2 : 1);
     }
     fence_mbar_init();
   }
@@ -283,6 +310,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  if (cl2) cluster_sync_all();   // both CTAs' mbarriers exist before either multicasts into / arrives on the other's
   pdl_wait();                 // the prologue above touched only weights / shared memory; activations from here on
   pdl_launch_dependents();
 
@@ -295,9 +323,9 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
       uint32_t abuf = 0, aph = 0, ws = 0, wph = 0;
       bool first = true;
       const int kb8 = p.KB / 8;
-      int chunk = blockIdx.x % p.n_chunks, tile = blockIdx.x / p.n_chunks;
-      const int dchunk = gridDim.x % p.n_chunks, dtile = gridDim.x / p.n_chunks;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = it_first; item < it_count; item += it_step) {
+        int chunk, tile;
+        item_of(item, chunk, tile);
         const int b = tile / p.tiles_per_b;
         const int r0 = (tile - b * p.tiles_per_b) * 128;
         const size_t in0 = (((size_t)b * p.Cin8 + (groups ? (size_t)chunk * p.n_cb * kb8 : 0)) * p.Tp_in + p.halo + r0 -
@@ -324,16 +352,22 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
               const int nt = min(p.JG, p.k - j0);
               const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
               if (!p.resident) mbar_wait(&w_empty[slot], wph ^ 1);
-              mbar_arrive_expect_tx(&w_full[slot], (uint32_t)nt * w_tap_bytes);
-              tma_load_1d(sW + (size_t)slot * w_slot_bytes, wchunk + ((size_t)cb * p.k + j0) * w_tap_bytes,
-                          (uint32_t)nt * w_tap_bytes, &w_full[slot]);
+              const uint32_t wbytes = ((uint32_t)nt * w_tap_bytes) >> p.exp_half_w;
+              mbar_arrive_expect_tx(&w_full[slot], wbytes);
+              const unsigned char* wsrc = wchunk + ((size_t)cb * p.k + j0) * w_tap_bytes;
+              if (cl2) {
+                // this CTA's half of the stage, into BOTH CTAs' slot; the partner delivers the other half
+                const uint32_t half = wbytes >> 1;
+                tma_load_1d_multicast(sW + (size_t)slot * w_slot_bytes + crank * half, wsrc + crank * half, half,
+                                      &w_full[slot], (uint16_t)3);
+              } else {
+                tma_load_1d(sW + (size_t)slot * w_slot_bytes, wsrc, wbytes, &w_full[slot]);
+              }
               if (++ws == (uint32_t)p.NS) { ws = 0; wph ^= 1; }
             }
           }
         }
         first = false;
-        chunk += dchunk; tile += dtile;
-        if (chunk >= p.n_chunks) { chunk -= p.n_chunks; ++tile; }
       }
     }
   } else if (warp == 1) {
@@ -348,7 +382,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
       const uint32_t a_lo_off = a_plane_bytes >> 4;
       uint32_t abuf = 0, aph = 0, ws = 0, wph = 0, ab = 0, accph = 0;
       bool first = true;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = it_first; item < it_count; item += it_step) {
         mbar_wait(&acc_empty[ab], accph ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base + ab * (uint32_t)p.acc_cols;
@@ -383,7 +417,12 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
                 accum = 1;
               }
             }
-            if (!p.resident) umma_commit(&w_empty[slot]);
+            if (!p.resident) {
+              if (cl2)
+                umma_commit_multicast(&w_empty[slot], (uint16_t)3);   // frees the slot in both CTAs of the pair
+              else
+                umma_commit(&w_empty[slot]);
+            }
             if (++ws == (uint32_t)p.NS) { ws = 0; wph ^= 1; }
           }
           umma_commit(&a_empty[abuf]);
@@ -402,9 +441,9 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
     const int row = quarter * 32 + lane;
     const int cout8 = p.Cout / 8;
     uint32_t ab = 0, accph = 0;
-    int chunk = blockIdx.x % p.n_chunks, tile = blockIdx.x / p.n_chunks;
-    const int dchunk = gridDim.x % p.n_chunks, dtile = gridDim.x / p.n_chunks;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int item = it_first; item < it_count; item += it_step) {
+      int chunk, tile;
+      item_of(item, chunk, tile);
       const int b = tile / p.tiles_per_b;
       const int r = (tile - b * p.tiles_per_b) * 128 + row;
       const int Tvalid = p.lengths ? min(p.T, p.lengths[b] * p.len_mul) : p.T;
@@ -543,13 +582,12 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ab]);
       if (++ab == (uint32_t)p.nbuf) { ab = 0; accph ^= 1; }
-      chunk += dchunk; tile += dtile;
-      if (chunk >= p.n_chunks) { chunk -= p.n_chunks; ++tile; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (cl2) cluster_sync_all();   // neither CTA leaves while the other may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
   }

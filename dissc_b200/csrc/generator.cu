@@ -204,6 +204,7 @@ static int g_tc_na_pref = -1, g_tc_split_w = 1;
 // 256-column GEMMs as two 128-column chunks (each with its own main + cross accumulators, double-buffered in TMEM)
 // instead of one 256-column chunk: -1 = env DISSC_TC_SPLIT256 or the default
 static int g_tc_split256 = -1;
+static int g_tc_cluster2 = -1;   // 2-CTA clusters with multicast weights (-1: env DISSC_TC_CLUSTER2 or the default 0)
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
 bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc) {
@@ -326,7 +327,8 @@ static int num_sms() {
 // before their first dependent global access.  DISSC_PDL=0 falls back to ordinary launches.
 static int g_pdl = -1;
 template <typename P>
-static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem, cudaStream_t st, const P& p) {
+static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem, cudaStream_t st, const P& p,
+                              int cluster = 1) {
   if (g_pdl < 0) {
     const char* e = getenv("DISSC_PDL");
     g_pdl = e ? (atoi(e) != 0) : 1;
@@ -336,11 +338,22 @@ static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem,
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
@@ -353,7 +366,7 @@ static int launch_conv_tc_inst(const TcParams& p, const TcLayer& L, int grid, cu
                                     (int)(kSmemPerSm - 1024)));
     attr_set[dev_] = true;
   }
-  DISSC_CUDA(launch_pdl(conv_tc_kernel<NC, EPW, MODE>, grid, tc_threads(EPW), L.smem, st, p));
+  DISSC_CUDA(launch_pdl(conv_tc_kernel<NC, EPW, MODE>, grid, tc_threads(EPW), L.smem, st, p, p.cluster2 ? 2 : 1));
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
@@ -399,6 +412,14 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.acc_cols = L.acc_cols; p.nbuf = L.nbuf; p.NA = L.NA;
   if (p.in_scale == 0.f) p.in_scale = 1.f;
   if (p.plane_scale == 0.f) p.plane_scale = 1.f;
+  {
+    static int half_w = -1;   // experiment switch, see TcParams::exp_half_w
+    if (half_w < 0) {
+      const char* e = getenv("DISSC_EXP_HALFW");
+      half_w = e ? atoi(e) : 0;
+    }
+    p.exp_half_w = (!L.resident && half_w > 0) ? half_w : 0;
+  }
   p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale / p.in_scale;   // powers of two: exact
   p.Cin8 = L.cin8_total ? L.cin8_total : L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
   p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
@@ -407,12 +428,27 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   for (int s = 3; s < 12; ++s)
     if ((1 << s) == L.Cout) p.cout_log2 = s;
   p.tiles_per_b = (rows + 127) / 128;
-  p.n_items = p.B * p.tiles_per_b * L.n_chunks;
-  const int grid = std::min(p.n_items, num_sms() * L.ctas_per_sm);
+  p.n_tiles = p.B * p.tiles_per_b;
+  p.n_items = p.n_tiles * L.n_chunks;
+  int grid = std::min(p.n_items, num_sms() * L.ctas_per_sm);
   const int mode = tc_mode(p, L);
   if (g_tc_epw64 < 0) {
     const char* e = getenv("DISSC_TC_EPW64");
     g_tc_epw64 = e ? atoi(e) : 8;
+  }
+  // 2-CTA clusters sharing one multicast weight stream: the 8-epilogue-warp kernels (one CTA per SM) with streamed weights
+  // and a dedicated weight-producer thread, when there are at least two tiles to pair up
+  if (g_tc_cluster2 < 0) {
+    const char* e = getenv("DISSC_TC_CLUSTER2");
+    g_tc_cluster2 = e ? (atoi(e) != 0) : 0;   // measured: no change (profiles/README.md r02) -> off by default
+  }
+  const bool epw8 = L.NC >= 128 || (L.NC == 64 && L.ctas_per_sm == 1 && g_tc_epw64 == 8 && mode != kTcGeneric);
+  p.cluster2 = 0;
+  if (g_tc_cluster2 && epw8 && !L.resident && L.split_w && L.ctas_per_sm == 1 && p.n_tiles >= 2 && !p.exp_half_w) {
+    const int pair_items = ((p.n_tiles + 1) / 2) * L.n_chunks;
+    grid = std::min(2 * pair_items, num_sms()) & ~1;
+    p.cluster2 = grid >= 2 ? 1 : 0;
+    if (!p.cluster2) grid = std::min(p.n_items, num_sms() * L.ctas_per_sm);
   }
   switch (L.NC) {
     case 16: return launch_conv_tc_mode<16, 4>(p, L, mode, grid, st);
@@ -503,9 +539,11 @@ static int launch_pair(PairParams p, const PairLayer& L, const TcLayer& c1, cons
 // fused ResBlock pair, C = 16, two samples per GEMM row (resblock_pack2_tc.cuh): plan + weights + launch
 // ------------------------------------------------------------------------
 static int g_use_pack2 = -1;  // DISSC_TC_PACK2=0 falls back to the one-sample-per-row pair kernel
+static int g_pack2_groups = -1;  // DISSC_TC_PACK2_GROUPS=2|3: tiles in flight per CTA (default 2)
 
 struct Pack2Layer {
   bool ok = false;
+  int G = 2;             // worker groups = tiles in flight per CTA
   int k = 0, dil = 1, S = 0, U = 0, M_out = 0;
   int base[kPack2MaxDil] = {}, n_out[kPack2MaxDil] = {};
   unsigned d_magic = 0;
@@ -543,10 +581,21 @@ static bool pack2_plan(int C, int k, int dil, Pack2Layer* L) {
     L->k = k; L->dil = dil; L->S = S; L->U = U; L->M_out = U - (k - 1);
     L->d_magic = (unsigned)(0xFFFFFFFFu / (unsigned)dil + 1u);   // ceil(2^32 / d); d = 1: wraps to 0, handled below
     const size_t stg = (size_t)2 * Lx * 32, tile = (size_t)2 * 4 * RX * 16, w = (size_t)S * 4096;
-    L->smem = 2 * stg + 4 * tile + 2 * w + 2 * 16 * 4 + 17 * 8 + 128;
-    if (L->smem > kSmemPerSm - 1536) return false;
-    L->ok = true;
-    return true;
+    if (g_pack2_groups < 0) {
+      const char* e = getenv("DISSC_TC_PACK2_GROUPS");
+      g_pack2_groups = e ? atoi(e) : 2;
+    }
+    // two tiles in flight (96 registers per thread).  Three fit in shared memory, but 26 warps leave 72 registers per
+    // thread: the kernel spills and the MRF-accumulate pairs get 25 % slower (profiles/README.md r02) -- opt-in only
+    for (int G = std::max(2, std::min(3, g_pack2_groups)); G >= 2; --G) {
+      L->smem = G * (stg + 2 * tile) + 2 * w + 2 * 16 * 4 + (8 * G + 1) * 8 + 128;
+      if (L->smem <= kSmemPerSm - 1536) {
+        L->G = G;
+        L->ok = true;
+        return true;
+      }
+    }
+    return false;
   }
   return false;
 }
@@ -566,7 +615,9 @@ static int launch_pack2(Pack2Params p, const Pack2Layer& L, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
   const int dev_ = current_device_slot();
   if (!attr_set[dev_]) {
-    DISSC_CUDA(cudaFuncSetAttribute(resblock_pack2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DISSC_CUDA(cudaFuncSetAttribute(resblock_pack2_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSmemPerSm - 1024)));
+    DISSC_CUDA(cudaFuncSetAttribute(resblock_pack2_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(kSmemPerSm - 1024)));
     attr_set[dev_] = true;
   }
@@ -580,7 +631,10 @@ static int launch_pack2(Pack2Params p, const Pack2Layer& L, cudaStream_t st) {
   p.tiles_per_b = (p.T + L.M_out - 1) / L.M_out;
   p.n_tiles = p.B * p.tiles_per_b;
   const int grid = std::min(p.n_tiles, num_sms());
-  DISSC_CUDA(launch_pdl(resblock_pack2_tc_kernel, grid, kPack2Threads, L.smem, st, p));
+  if (L.G == 3)
+    DISSC_CUDA(launch_pdl(resblock_pack2_tc_kernel<3>, grid, pack2_threads(3), L.smem, st, p));
+  else
+    DISSC_CUDA(launch_pdl(resblock_pack2_tc_kernel<2>, grid, pack2_threads(2), L.smem, st, p));
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
@@ -1579,6 +1633,7 @@ int dissc_tc_set_tuning(int key, int value) {
     case 0: dissc::g_tc_na_pref = value; return DISSC_OK;
     case 1: dissc::g_tc_split_w = value ? 1 : 0; return DISSC_OK;
     case 2: dissc::g_tc_split256 = value ? 1 : 0; return DISSC_OK;
+    case 3: dissc::g_tc_cluster2 = value ? 1 : 0; return DISSC_OK;
   }
   return dissc::set_err(DISSC_EINVAL, "unknown tuning key %d", key);
 }

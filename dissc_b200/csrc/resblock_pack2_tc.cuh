@@ -28,7 +28,8 @@
 namespace dissc {
 
 constexpr int kPack2MaxDil = 8;
-constexpr int kPack2Threads = 64 + 2 * 8 * 32;   // producer, MMA issuer, two worker groups of 8 warps
+// producer warp, MMA-issuer warp, G worker groups of 8 warps (one tile in flight per group)
+__host__ __device__ constexpr int pack2_threads(int G) { return 64 + G * 8 * 32; }
 
 struct Pack2Params {
   const float* x;       // f32h [B][2][Tpf][8]
@@ -57,7 +58,9 @@ struct Pack2Params {
   float plane_slope, plain_slope;
 };
 
-__global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(const Pack2Params p) {
+template <int G>
+__global__ void __launch_bounds__(pack2_threads(G), 1) resblock_pack2_tc_kernel(const Pack2Params p) {
+  constexpr int kPack2Threads = pack2_threads(G);
   constexpr int C = 16, C8 = 2;            // real channels
   constexpr int NG = 32, G8 = 4, KS = 2;   // GEMM width (two samples x C), its 8-wide K groups, its 16-wide K steps
   constexpr int WPG = 8, CH = 2;
@@ -73,28 +76,28 @@ __global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(con
   const uint32_t xop_plane = (uint32_t)G8 * RX * 16, xop_bytes = 2 * xop_plane;
   const uint32_t xt_plane = xop_plane, xt_bytes = xop_bytes;
   const uint32_t w_bytes = (uint32_t)S * w_tap_bytes;
-  unsigned char* sStg = smem_raw;                   // [2][stg_bytes]
-  unsigned char* sXop = sStg + 2 * stg_bytes;       // [2][xop_bytes]
-  unsigned char* sXt = sXop + 2 * xop_bytes;        // [2][xt_bytes]
-  unsigned char* sW1 = sXt + 2 * xt_bytes;
+  unsigned char* sStg = smem_raw;                   // [G][stg_bytes]
+  unsigned char* sXop = sStg + G * stg_bytes;       // [G][xop_bytes]
+  unsigned char* sXt = sXop + G * xop_bytes;        // [G][xt_bytes]
+  unsigned char* sW1 = sXt + G * xt_bytes;
   unsigned char* sW2 = sW1 + w_bytes;
   float* s_b1 = reinterpret_cast<float*>(sW2 + w_bytes);
   float* s_b2 = s_b1 + C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_b2 + C);
-  uint64_t* stg_full = bars;         // [2]
-  uint64_t* stg_empty = bars + 2;    // [2]
-  uint64_t* xop_full = bars + 4;     // [2]
-  uint64_t* xop_empty = bars + 6;    // [2]
-  uint64_t* acc1_full = bars + 8;    // [2]
-  uint64_t* xt_full = bars + 10;     // [2]
-  uint64_t* acc2_full = bars + 12;   // [2]
-  uint64_t* acc2_empty = bars + 14;  // [2]
-  uint64_t* w_full = bars + 16;      // [1]
+  uint64_t* stg_full = bars;             // [G]
+  uint64_t* stg_empty = bars + G;        // [G]
+  uint64_t* xop_full = bars + 2 * G;     // [G]
+  uint64_t* xop_empty = bars + 3 * G;    // [G]
+  uint64_t* acc1_full = bars + 4 * G;    // [G]
+  uint64_t* xt_full = bars + 5 * G;      // [G]
+  uint64_t* acc2_full = bars + 6 * G;    // [G]
+  uint64_t* acc2_empty = bars + 7 * G;   // [G]
+  uint64_t* w_full = bars + 8 * G;       // [1]
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < G; ++i) {
       mbar_init(&stg_full[i], 1);
       mbar_init(&stg_empty[i], WPG);
       mbar_init(&xop_full[i], WPG);
@@ -113,11 +116,12 @@ __global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(con
   }
   // every operand slot the convert step / epilogue 1 never writes (odd phase tails, rows past the data that only
   // discarded output rows read) must hold finite values: zero both operand tile pairs once
-  for (int i = tid; i < (int)((2 * xop_bytes + 2 * xt_bytes) / 16); i += kPack2Threads)
+  for (int i = tid; i < (int)((G * xop_bytes + G * xt_bytes) / 16); i += kPack2Threads)
     reinterpret_cast<uint4*>(sXop)[i] = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(G <= 2 ? 256 : 512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -134,9 +138,8 @@ __global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(con
       mbar_arrive_expect_tx(&w_full[0], 2 * w_bytes);
       tma_load_1d(sW1, p.w1, w_bytes, &w_full[0]);
       tma_load_1d(sW2, p.w2, w_bytes, &w_full[0]);
-      uint32_t s = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++s) {
-        const uint32_t g = s & 1, ph = (s >> 1) & 1;
+      uint32_t g = 0, ph = 0;   // tile s of this CTA belongs to group s % G, its phase is (s / G) & 1
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_b;
         const int t0 = (tile - b * p.tiles_per_b) * M_out;
         mbar_wait(&stg_empty[g], ph ^ 1);
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(con
         for (int c8 = 0; c8 < C8; ++c8)
           tma_load_1d(sStg + g * stg_bytes + (size_t)c8 * Lx * 32, src + (size_t)c8 * p.Tpf * 8, (uint32_t)Lx * 32,
                       &stg_full[g]);
+        if (++g == (uint32_t)G) { g = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -171,22 +175,26 @@ __global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(con
       };
       int n_mine = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_mine;
-      for (int s = 0; s <= n_mine; ++s) {
+      // conv1 runs kLead tiles ahead of conv2: conv1(s), conv2(s - kLead), conv1(s + 1), ... so a tile's epilogue 1 has
+      // kLead conv1's worth of tensor time before the MMA thread needs its xt
+      constexpr int kLead = G - 1;
+      uint32_t g1 = 0, ph1 = 0, g2 = 0, ph2 = 0;
+      for (int s = 0; s < n_mine + kLead; ++s) {
         if (s < n_mine) {
-          const uint32_t g = s & 1, ph = (s >> 1) & 1;
-          mbar_wait(&xop_full[g], ph);
+          mbar_wait(&xop_full[g1], ph1);
           tc_fence_after();
-          conv(smem_u32(sXop + g * xop_bytes), w1d, tmem_base + g * 4u * NG);
-          umma_commit(&xop_empty[g]);
-          umma_commit(&acc1_full[g]);
+          conv(smem_u32(sXop + g1 * xop_bytes), w1d, tmem_base + g1 * 4u * NG);
+          umma_commit(&xop_empty[g1]);
+          umma_commit(&acc1_full[g1]);
+          if (++g1 == (uint32_t)G) { g1 = 0; ph1 ^= 1; }
         }
-        if (s >= 1) {
-          const uint32_t sp = (uint32_t)(s - 1), g = sp & 1, ph = (sp >> 1) & 1;
-          mbar_wait(&xt_full[g], ph);
-          mbar_wait(&acc2_empty[g], ph ^ 1);
+        if (s >= kLead) {
+          mbar_wait(&xt_full[g2], ph2);
+          mbar_wait(&acc2_empty[g2], ph2 ^ 1);
           tc_fence_after();
-          conv(smem_u32(sXt + g * xt_bytes), w2d, tmem_base + g * 4u * NG + 2u * NG);
-          umma_commit(&acc2_full[g]);
+          conv(smem_u32(sXt + g2 * xt_bytes), w2d, tmem_base + g2 * 4u * NG + 2u * NG);
+          umma_commit(&acc2_full[g2]);
+          if (++g2 == (uint32_t)G) { g2 = 0; ph2 ^= 1; }
         }
       }
     }
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(con
       }
     };
     uint32_t it = 0;
-    const int first = blockIdx.x + g * gridDim.x, step = 2 * gridDim.x;
+    const int first = blockIdx.x + g * gridDim.x, step = G * gridDim.x;
     if (first < p.n_tiles) convert(first, 0);
     for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
       const uint32_t ph = it & 1;
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(kPack2Threads, 1) resblock_pack2_tc_kernel(con
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G <= 2 ? 256 : 512));
   }
 }
 
