@@ -204,6 +204,7 @@ static int g_tc_na_pref = -1, g_tc_split_w = 1;
 // 256-column GEMMs as two 128-column chunks (each with its own main + cross accumulators, double-buffered in TMEM)
 // instead of one 256-column chunk: -1 = env DISSC_TC_SPLIT256 or the default
 static int g_tc_split256 = -1;
+extern int g_hub_attn_tc;        // hubert.cu: tensor-core attention (key 4)
 static int g_tc_cluster2 = -1;   // 2-CTA clusters with multicast weights (-1: env DISSC_TC_CLUSTER2 or the default 0)
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
@@ -1634,6 +1635,7 @@ int dissc_tc_set_tuning(int key, int value) {
     case 1: dissc::g_tc_split_w = value ? 1 : 0; return DISSC_OK;
     case 2: dissc::g_tc_split256 = value ? 1 : 0; return DISSC_OK;
     case 3: dissc::g_tc_cluster2 = value ? 1 : 0; return DISSC_OK;
+    case 4: dissc::g_hub_attn_tc = value ? 1 : 0; return DISSC_OK;
   }
   return dissc::set_err(DISSC_EINVAL, "unknown tuning key %d", key);
 }

@@ -343,6 +343,229 @@ __global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* q
   }
 }
 
+// ---- attention on the tensor cores ---------------------------------------------------------------------------------
+// One CTA = one (clip, head, 128-query tile); T <= kAttnTcKeys keys (a 160 000-sample clip has 499 frames: those
+// batches keep the CUDA-core kernel above).  Inputs are the split-fp16 planes of the fused QKV projection
+// [B][3*D8][Tp][8] (q already scaled by head_dim^-0.5), i.e. exactly the K-major UMMA operand layout for Q (A: rows =
+// queries) and K (B: rows = keys), so both tiles arrive by bulk TMA:
+//   S = Q K^T        128 x 320, three split-precision MMAs per 16 dims into ONE TMEM accumulator (12 accumulations)
+//   softmax          thread r owns query row r = TMEM lane r: two passes over its 320 scores (max; exp + sum), keys
+//                    >= the clip's valid length masked; P written as fp16 hi/lo K-major tiles over the dead K tile
+//   O = P V          V transposed on chip ([keys][dims] planes -> K-major [key group][hi|lo][dim][8 keys]) while the
+//                    S MMAs run; per 160-key block  P_hi x [V_hi|V_lo] -> [main|cross],  P_lo x V_hi -> cross
+//   out              (main + cross) / sum -> fp16 hi/lo planes [B][D8][Tp][8] (the out-projection's operand)
+// fp32-accurate like every other GEMM here (the units must not move), at tensor-core instead of FMA-pipe speed.
+int g_hub_attn_tc = -1;               // dissc_tc_set_tuning key 4 / env DISSC_HUB_ATTN_TC (default 1)
+constexpr int kAttnTcKeys = 320;      // keys per CTA (multiple of 16, two N = 160 chunks for S)
+constexpr int kAttnTcThreads = 256;
+constexpr uint32_t kVtStride = 2048 + 16;                    // bytes between key groups of the V^T tile (bank padding)
+constexpr size_t kAttnTcSmem = 32768 + 81920 + (kAttnTcKeys / 8) * kVtStride + 64;   // Q | K (later P) | V^T | barriers
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(const __half* q_hi, const __half* q_lo,
+                                                                            const int* lengths, int D8, int T, int Tp_in,
+                                                                            int Tp, int halo, __half* out_hi, __half* out_lo) {
+  constexpr int NK = kAttnTcKeys, NKB = NK / 2;          // keys, keys per P block
+  constexpr uint32_t kQPlane = 8 * 128 * 16;             // one plane of the Q tile: [c8][128 rows][16 B]
+  constexpr uint32_t kKPlane = 8 * NK * 16;              // K tile: [c8][320 rows][16 B]
+  constexpr uint32_t kPPlane = (NKB / 8) * 128 * 16;     // P block: [key group (20)][128 rows][16 B]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sQ = smem_raw;                          // hi plane, lo plane
+  unsigned char* sK = sQ + 2 * kQPlane;                  // hi plane, lo plane; reused for P (hi block, lo block)
+  unsigned char* sV = sK + 2 * kKPlane;                  // V^T: [key group (40), stride kVtStride][hi|lo][64 dims][16 B = 8 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + (NK / 8) * kVtStride);
+  uint64_t* qk_full = bars;      // TMA: Q and K tiles landed
+  uint64_t* mma_done = bars + 1; // tcgen05.commit after S, after each PV block
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_red[2][128];   // per-row partial max / sum of the two threads that share a row
+  // two threads per query row: thread r and thread r + 128 (warps w and w + 4 address the same TMEM lane quarter) take
+  // alternate 32-key chunks of every pass and alternate halves of the output
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, hsel = tid >> 7;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+  const int Tv = lengths ? min(T, lengths[b]) : T;
+  if (tid == 0) {
+    mbar_init(qk_full, 1);
+    mbar_init(mma_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const size_t slab = (size_t)Tp_in * 8;                                   // halves per (b, c8) slab of the QKV planes
+  const size_t base_q = ((size_t)b * 3 * D8 + h * 8) * slab + (size_t)halo * 8;
+  const size_t base_k = base_q + (size_t)D8 * slab, base_v = base_q + (size_t)2 * D8 * slab;
+  constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)((NK / 2) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = 160
+  constexpr uint32_t idesc_o2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);       // N = 128
+  constexpr uint32_t idesc_o1 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);        // N = 64
+  if (warp == 0 && elect_one()) {
+    // ---- Q / K tiles by bulk TMA, then S = Q K^T (hi*hi + hi*lo + lo*hi into one accumulator, TMEM columns [0, 320))
+    mbar_arrive_expect_tx(qk_full, 2 * kQPlane + 2 * kKPlane);
+    for (int c8 = 0; c8 < 8; ++c8) {
+      tma_load_1d(sQ + c8 * 2048, q_hi + base_q + c8 * slab + (size_t)q0 * 8, 2048, qk_full);
+      tma_load_1d(sQ + kQPlane + c8 * 2048, q_lo + base_q + c8 * slab + (size_t)q0 * 8, 2048, qk_full);
+      tma_load_1d(sK + c8 * (NK * 16), q_hi + base_k + c8 * slab, NK * 16, qk_full);
+      tma_load_1d(sK + kKPlane + c8 * (NK * 16), q_lo + base_k + c8 * slab, NK * 16, qk_full);
+    }
+    mbar_wait(qk_full, 0);
+    tc_fence_after();
+    const uint32_t qd = umma_desc_lo(smem_u32(sQ), 2048), kd = umma_desc_lo(smem_u32(sK), NK * 16);
+    const uint32_t q_lo_off = kQPlane >> 4, k_lo_off = kKPlane >> 4;
+    for (int nch = 0; nch < 2; ++nch) {
+      const uint32_t d = tmem_base + nch * (NK / 2);
+      const uint32_t kdn = kd + ((uint32_t)(nch * (NK / 2) * 16) >> 4);
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t qa = qd + ks * ((2 * 2048) >> 4), ka = kdn + ks * ((2 * NK * 16) >> 4);
+        umma_f16(d, umma_desc(qa), umma_desc(ka), idesc_s, ks > 0);
+        umma_f16(d, umma_desc(qa), umma_desc(ka + k_lo_off), idesc_s, 1);
+        umma_f16(d, umma_desc(qa + q_lo_off), umma_desc(ka), idesc_s, 1);
+      }
+    }
+    umma_commit(mma_done);
+  }
+  __syncwarp();
+  // ---- meanwhile: V^T.  A thread transposes one 8-key x 8-dim block per plane in registers: eight 16-byte global
+  //      loads (8 consecutive keys of one 8-dim slab: 128 contiguous bytes, lanes = consecutive key groups), 32 byte
+  //      permutes, eight 16-byte shared stores (one per dim: its 8 keys).  The key-group stride of the V^T tile is padded
+  //      to 2048 + 16 bytes so the 8 lanes of a store phase hit 8 different 16-byte bank groups.
+  for (int item = tid; item < (NK / 8) * 8; item += kAttnTcThreads) {
+    const int c8 = item / (NK / 8), kg = item - c8 * (NK / 8);
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      const __half* src = (pl ? q_lo : q_hi) + base_v + c8 * slab + (size_t)kg * 64;
+      uint4 a[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        a[kk] = (kg * 8 + kk < Tv) ? *reinterpret_cast<const uint4*>(src + kk * 8) : make_uint4(0, 0, 0, 0);
+      unsigned char* dst = sV + (size_t)kg * kVtStride + pl * 1024 + (size_t)(c8 * 8) * 16;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {       // dim n of the slab: its 8 keys, two per word
+        const uint32_t sel = (n & 1) ? 0x7632u : 0x5410u;
+        uint32_t o[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t lo_w = (n >> 1) == 0 ? a[2 * w].x : (n >> 1) == 1 ? a[2 * w].y : (n >> 1) == 2 ? a[2 * w].z : a[2 * w].w;
+          const uint32_t hi_w = (n >> 1) == 0 ? a[2 * w + 1].x : (n >> 1) == 1 ? a[2 * w + 1].y : (n >> 1) == 2 ? a[2 * w + 1].z
+                                                                                                                : a[2 * w + 1].w;
+          o[w] = __byte_perm(lo_w, hi_w, sel);
+        }
+        *reinterpret_cast<uint4*>(dst + n * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  // ---- softmax: query row = TMEM lane; pass 1: row maximum over the valid keys
+  mbar_wait(mma_done, 0);
+  __syncwarp();               // tcgen05.ld is warp-collective
+  tc_fence_after();
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  float mx = -INFINITY;
+  for (int c0 = hsel * 32; c0 < NK; c0 += 64) {
+    if (c0 >= Tv) break;
+    float sc[32];
+    tmem_ld32(lane_addr + c0, sc);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i < Tv) mx = fmaxf(mx, sc[i]);
+  }
+  s_red[hsel][row] = mx;
+  __syncthreads();
+  mx = fmaxf(s_red[0][row], s_red[1][row]);
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float mxl = mx * kLog2e;
+  float l = 0.f;
+  uint32_t done_phase = 1;
+  const uint32_t pd = umma_desc_lo(smem_u32(sK), 128 * 16), vd = umma_desc_lo(smem_u32(sV), kVtStride);
+  for (int blk = 0; blk < 2; ++blk) {
+    // P block = keys [blk*160, blk*160 + 160): exp(s - max), fp16 hi / lo, K-major [key group][row][8 keys]
+    for (int ci = hsel; ci < NKB / 32; ci += 2) {
+      const int c0 = blk * NKB + ci * 32;
+      float sc[32];
+      if (c0 < Tv) {
+        tmem_ld32(lane_addr + c0, sc);
+        tmem_ld_wait();
+      }
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int key = c0 + g8 * 8 + i;
+          // exp(s - max) as one FFMA + ex2.approx (relative error 2^-22, far inside the fp16 hi / lo split of P)
+          pv[i] = (key < Tv) ? exp2f(fmaf(sc[g8 * 8 + i], kLog2e, -mxl)) : 0.f;
+          l += pv[i];
+        }
+        unsigned char* dst = sK + (size_t)(ci * 4 + g8) * 2048 + row * 16;
+        split_store8(reinterpret_cast<__half*>(dst), reinterpret_cast<__half*>(dst + kPPlane), pv);
+      }
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+      const uint32_t d = tmem_base + NK;   // O accumulator: [main 64 | cross 64]
+      for (int ks = 0; ks < NKB / 16; ++ks) {
+        const uint32_t pa = pd + ks * ((2 * 2048) >> 4);
+        const uint32_t va = vd + (uint32_t)(blk * (NKB / 8) + 2 * ks) * (kVtStride >> 4);
+        umma_f16(d, umma_desc(pa), umma_desc(va), idesc_o2, (blk | ks) != 0);                 // P_hi x [V_hi|V_lo]
+        umma_f16(d + 64, umma_desc(pa + (kPPlane >> 4)), umma_desc(va), idesc_o1, 1);          // P_lo x V_hi -> cross
+      }
+      umma_commit(mma_done);
+    }
+    __syncwarp();
+    mbar_wait(mma_done, done_phase);   // the P buffer may be overwritten / O is complete
+    done_phase ^= 1;
+    __syncwarp();
+    tc_fence_after();
+  }
+  s_red[hsel][row] = l;
+  __syncthreads();
+  l = s_red[0][row] + s_red[1][row];
+  // ---- O / l -> planes (this thread's 32 of the row's 64 dims)
+  {
+    const int t = q0 + row;
+    const float inv = (t < Tv && l > 0.f) ? 1.f / l : 0.f;
+    const uint32_t o_addr = lane_addr + NK + hsel * 32;
+    float om[32], oc[32];
+    tmem_ld32(o_addr, om);
+    tmem_ld32(o_addr + 64, oc);
+    tmem_ld_wait();
+    if (t < T) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (om[c * 8 + e] + oc[c * 8 + e]) * inv;
+        const size_t off = (((size_t)b * D8 + h * 8 + hsel * 4 + c) * Tp + halo + t) * 8;
+        split_store8(out_hi + off, out_lo + off, y);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ---- k-means assignment ----------------------------------------------------------------------------------------------
 // one warp per frame; x f32b [B][D8][Tr][8]; centroids (K, D) row-major; units int64 (B, T) (-1 past the valid length)
 // A warp assigns kKmFrames consecutive frames at once: every centroid value it loads from L2 is used for all of them
@@ -570,7 +793,7 @@ struct HubBuffers {
   __half* dA[2];  // de-interleaved plane pairs (hi at [0], lo at hi + plane_elems)
   __half* dB[2];
   float *X6, *X7, *X8, *H, *Y, *QKV;
-  __half *P6[2], *P7[2], *PH[2], *PA[2], *PF[2];
+  __half *P6[2], *P7[2], *PH[2], *PA[2], *PF[2], *PQ[2];   // PQ: planes of the fused QKV projection (tensor-core attention)
   size_t total;
 };
 
@@ -604,6 +827,7 @@ static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
     b.PH[i] = (__half*)bp.take(plane_bytes(D, T));
     b.PA[i] = (__half*)bp.take(plane_bytes(D, T));
     b.PF[i] = (__half*)bp.take(plane_bytes(c.ffn_dim, T));
+    b.PQ[i] = (__half*)bp.take(plane_bytes(3 * D, T));
   }
   b.total = bp.off;
   return b;
@@ -858,15 +1082,35 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
   }
   HUB_TRY(launch_zero_halos(bf.PF[0], bf.PF[1], B * c.ffn_dim / 8, Tp, T, st, kHubHalo));
   HUB_TRY(hub_layernorm(bf.X8, g->eln_w, g->eln_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
+  // attention on the tensor cores when all keys of a clip fit one CTA (<= 320 frames = 102 000 samples; BASELINE
+  // configs[3] clips have 299); longer batches use the CUDA-core kernel.  DISSC_HUB_ATTN_TC=0 forces the latter.
+  if (g_hub_attn_tc < 0) {
+    const char* e = getenv("DISSC_HUB_ATTN_TC");
+    g_hub_attn_tc = e ? (atoi(e) != 0) : 1;
+  }
+  const bool attn_tc = g_hub_attn_tc && T <= kAttnTcKeys;
+  if (attn_tc) DISSC_CUDA(cudaFuncSetAttribute(hub_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnTcSmem));
   for (int l = 0; l < c.n_layers; ++l) {
     const HubLayer& Ly = g->layers[l];
     {
       TcParams p = base();
-      p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = Ly.qkv_b; p.out_f32b = bf.QKV;
+      p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = Ly.qkv_b;
+      if (attn_tc) {
+        // planes for the tensor-core attention; leaky-relu with slope 1 is the identity (max(v, v * 1)) and keeps the
+        // specialised epilogue
+        p.out_hi = bf.PQ[0]; p.out_lo = bf.PQ[1]; p.plane_act = 1; p.plane_slope = 1.0f;
+      } else {
+        p.out_f32b = bf.QKV;
+      }
       HUB_TRY(launch_conv_tc(p, Ly.qkv, T, st));
     }
-    hub_attention_kernel<<<dim3((T + kAttnQ - 1) / kAttnQ, c.n_heads, B), kAttnQ, 0, st>>>(bf.QKV, lenT, D / 8, T, Tr, Tp, kHubHalo,
-                                                                               bf.PA[0], bf.PA[1]);
+    if (attn_tc) {
+      hub_attention_tc_kernel<<<dim3((T + 127) / 128, c.n_heads, B), kAttnTcThreads, kAttnTcSmem, st>>>(
+          bf.PQ[0], bf.PQ[1], lenT, D / 8, T, Tp, Tp, kHubHalo, bf.PA[0], bf.PA[1]);
+    } else {
+      hub_attention_kernel<<<dim3((T + kAttnQ - 1) / kAttnQ, c.n_heads, B), kAttnQ, 0, st>>>(bf.QKV, lenT, D / 8, T, Tr, Tp,
+                                                                                           kHubHalo, bf.PA[0], bf.PA[1]);
+    }
     DISSC_CUDA(cudaGetLastError());
     {
       TcParams p = base();

@@ -160,7 +160,8 @@ int dissc_tc_set_single_accumulator(int enable);
  * key 0 = number of activation buffers of the streamed-weight layers (2..4; 0 = heuristic), key 1 = separate
  * weight-producer thread in the N >= 128 kernels (0 / 1), key 2 = 256-column GEMMs as two 128-column chunks (1, default)
  * or one 256-column chunk (0), key 3 = 2-CTA clusters that share one multicast weight stream in the streamed-weight
- * kernels (0 = off, default: measured neutral; read at launch time).  No reference counterpart. */
+ * kernels (0 = off, default: measured neutral; read at launch time), key 4 = HuBERT attention on the tensor cores for
+ * clips of <= 320 frames (1, default) or always the fp32 CUDA-core kernel (0).  No reference counterpart. */
 int dissc_tc_set_tuning(int key, int value);
 
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */

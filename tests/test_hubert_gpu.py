@@ -128,6 +128,50 @@ def test_config4_clip_lengths_vs_transformers(cuda_device):
     print(f"hubert 96k/160k/32k: feature max-abs err {worst:.2e}; units agree with the fp64 oracle {agree}/{total}")
 
 
+def test_attention_tensor_core_path_at_config4_length(cuda_device):
+    """96 000-sample clips (299 frames: BASELINE configs[3]) take the tcgen05 attention kernel (<= 320 keys per CTA): a
+    ragged batch vs the fp64 oracle, and vs the fp32 CUDA-core attention on the same inputs (both within the feature
+    tolerance of the oracle; units per _unit_checks)."""
+    pytest.importorskip("transformers")
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_hubert as mg
+    from dissc_b200 import _lib
+    from dissc_b200.hubert import SpeechEncoder
+    model = mg.build_model()
+    sd = ho.from_transformers(model, 6)
+    g = torch.Generator().manual_seed(11)
+    lens = [96000, 70001, 96000, 400, 33333]
+    clips = [0.1 * torch.randn(n, generator=g) for n in lens]
+    feats64 = [ho.extract_features(sd, c.view(1, -1), 6, dtype=torch.float64)[0] for c in clips]
+    allf = torch.cat(feats64, 0).float()
+    cent = allf[torch.randperm(allf.shape[0], generator=g)[:100]] + 0.02 * torch.randn(100, 768, generator=g)
+    wave = torch.full((len(clips), max(lens)), -2.0)
+    for b, c in enumerate(clips):
+        wave[b, :len(c)] = c
+    out = {}
+    try:
+        for mode in (1, 0):
+            _lib.check(_lib.lib().dissc_tc_set_tuning(4, mode))
+            enc = SpeechEncoder.from_state_dict(sd, cent).to(cuda_device)
+            units, n_frames, dense = enc.encode_batch(wave.to(cuda_device), torch.tensor(lens, dtype=torch.int32))
+            out[mode] = (units.cpu(), n_frames.cpu(), dense.cpu())
+    finally:
+        _lib.lib().dissc_tc_set_tuning(4, 1)
+    for mode, (units, n_frames, dense) in out.items():
+        worst = 0.0
+        for b, f64 in enumerate(feats64):
+            T = ho.num_frames(lens[b])
+            assert int(n_frames[b]) == T
+            worst = max(worst, (dense[b, :T].double() - f64).abs().max().item())
+            assert torch.all(units[b, T:] == -1) and torch.all(dense[b, T:] == 0)
+            _unit_checks(units[b, :T], dense[b, :T], f64, cent, f"mode {mode} clip {b}")
+        print(f"attention {'tcgen05' if mode else 'fp32 CUDA-core'}: feature max-abs err vs fp64 oracle {worst:.2e}")
+        assert worst < 2e-4, (mode, worst)
+    assert (out[1][2] - out[0][2]).abs().max().item() < 2e-4
+
+
 def test_call_surface_matches_data_encode(cuda_device, setup):
     from dissc_b200.hubert import SpeechEncoder
     sd, lens, waves, feats, cent = setup
