@@ -325,7 +325,8 @@ def main():
     fam = {}
     for name, ms, fl, by in rows:
         key = "conv_tc_kernel" if name.endswith(".tc") else "resblock_pair_tc_kernel" if name.endswith(".ptc") \
-            else "resblock_pair64_tc_kernel" if name.endswith(".p64") else "conv_post_kernel" if name == "conv_post" \
+            else "resblock_pair64_tc_kernel" if name.endswith(".p64") else "resblock_pack2_tc_kernel" \
+            if name.endswith(".pk2") else "conv_post_kernel" if name == "conv_post" \
             else "convt1d_kernel" if name.startswith("ups") else "tc_embed_planes+tc_zero_halos" \
             if name in ("embed", "zero_halos") else "conv1d_fused_kernel"
         a = fam.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
@@ -342,7 +343,8 @@ def main():
         del a["flops"], a["bytes"]
     dom_name = max(fam, key=lambda k: fam[k]["ms"])
     dom = fam[dom_name]
-    sfx = {"conv_tc_kernel": ".tc", "resblock_pair_tc_kernel": ".ptc", "resblock_pair64_tc_kernel": ".p64"}.get(dom_name, "")
+    sfx = {"conv_tc_kernel": ".tc", "resblock_pair_tc_kernel": ".ptc", "resblock_pair64_tc_kernel": ".p64",
+           "resblock_pack2_tc_kernel": ".pk2"}.get(dom_name, "")
     dom_rows = [r for r in rows if r[0].endswith(sfx)]
     dom_bytes = sum(r[3] for r in dom_rows)
     dom_ms = sum(r[1] for r in dom_rows)

@@ -203,6 +203,7 @@ static int g_single_acc256 = -1;   // -1: env DISSC_TC_SINGLE_ACC or the default
 static int g_tc_na_pref = -1, g_tc_split_w = 1;
 // 256-column GEMMs as two 128-column chunks (each with its own main + cross accumulators, double-buffered in TMEM)
 // instead of one 256-column chunk: -1 = env DISSC_TC_SPLIT256 or the default
+static int g_tc_kb64 = -1;       // 64-channel activation blocks for the NC = 128 kernels (env DISSC_TC_KB64)
 static int g_tc_split256 = -1;
 extern int g_hub_attn_tc;        // hubert.cu: tensor-core attention (key 4)
 static int g_tc_cluster2 = -1;   // 2-CTA clusters with multicast weights (-1: env DISSC_TC_CLUSTER2 or the default 0)
@@ -236,6 +237,14 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
   L->Cin = Cin; L->Cin_pad = (Cin + 15) / 16 * 16; L->NC = NC; L->n_chunks = ncols / NC;
   L->k = taps; L->dil = dil; L->pad = pad;
   L->KB = (L->Cin_pad % 32 == 0) ? 32 : 16;
+  // streamed-weight 128-column kernels: 64-channel activation blocks halve the number of barrier round trips per MMA
+  // cycle (a block = k taps x 4 k-steps, a weight stage = one 32 KB tap), which is what the one-chunk 256-column
+  // configuration has and why it was faster (profiles/README.md r02)
+  if (g_tc_kb64 < 0) {
+    const char* e = getenv("DISSC_TC_KB64");
+    g_tc_kb64 = e ? (atoi(e) != 0) : 1;
+  }
+  if (g_tc_kb64 && NC == 128 && L->Cin_pad % 64 == 0 && L->Cin_pad >= 128) L->KB = 64;
   L->n_cb = L->Cin_pad / L->KB;
   L->single_acc = (NC == 256) ? g_single_acc256 : 0;
   L->acc_cols = L->single_acc ? NC : 2 * NC;
@@ -302,9 +311,10 @@ bool tc_plan_conv(int Cin, int Cout, int k, int dil, TcLayer* L) {
 static bool tc_plan_convt(int Cin, int Cout, int k, int u, TcLayer* L) {
   if (Cout % 8 || Cout > 256 || u < 1) return false;
   const int M = (k + u - 1) / u;
-  // a chunk holds whole output phases (NC % Cout == 0): 256-channel upsamplers keep 256-column chunks
-  if (!tc_plan(Cin, u * Cout, M, 1, M - 1, L, kTcHalo, Cout == 256 ? 256 : 0)) return false;
-  if (L->NC % Cout) { L->ok = false; return false; }
+  if (!tc_plan(Cin, u * Cout, M, 1, M - 1, L, kTcHalo)) return false;
+  // a chunk holds whole output phases, or a phase spans whole chunks (the epilogue derives phase and channel from the
+  // global column index either way)
+  if (L->NC % Cout && Cout % L->NC) { L->ok = false; return false; }
   L->Cout = Cout; L->up = u; L->up_P = L->NC / Cout; L->up_pad = (k - u) / 2;
   return true;
 }
