@@ -11,7 +11,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
    --log-file gpurun_out/r02_launches.csv python scripts/one_forward.py 64 300 1 > gpurun_out/r02_ncu_list.log 2>&1
 python scripts/ncu_traffic.py gpurun_out/r02_launches.csv gpurun_out/r02_traffic.json | tail -12
 # full captures: stage-4 k=11 packed pair (MMA N = 64 / 32), stage-1 k=11 conv, stage-0 k=11 conv (two 128-column chunks)
-for spec in "resblock_pack2 6 s4k11_pack2" "resblock_pack2 0 s4k3_pack2" "conv_tc_kernel 61 s1k11c1" "conv_tc_kernel 16 s0k11c1"; do
+for spec in "resblock_pack2 6 s4k11_pack2" "resblock_pack2 0 s4k3_pack2" "conv_tc_kernel 33 s1k11c1" "conv_tc_kernel 14 s0k11c1"; do
   set -- $spec
   timeout 600 ncu --set full --import-source on --clock-control none -k regex:$1 --launch-skip $2 --launch-count 1 \
     -o /tmp/c_$3 -f python scripts/one_forward.py 64 300 1 > gpurun_out/ncu_c_$3.log 2>&1
