@@ -122,12 +122,13 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 // Embedding-row ids come from the caller (unit ids from a k-means model, speaker ids from a manifest): nn.Embedding
 // raises on an id outside the table (device assert on CUDA); here the gather stays inside the table (row 0 is read
-// instead) and the handle's error flag -- an int in mapped pinned host memory -- is set, which the next host-synchronous
-// entry point (dissc_*_status, dissc_gen_forward_host) turns into DISSC_EINDEX.
+// instead) and the handle's error flags -- two ints in mapped pinned host memory, one per kind of id -- are set, which the
+// next host-synchronous entry point (dissc_*_status, dissc_gen_forward_host) turns into DISSC_EINDEX.  Plain stores of a
+// constant: atomics on host memory need PCIe atomics, which the platform need not provide (compute-sanitizer flags them).
 enum { kIdxUnit = 1, kIdxSpeaker = 2 };
 __device__ __forceinline__ long long checked_row(long long id, int rows, int* err_flag, int what) {
   if ((unsigned long long)id >= (unsigned long long)rows) {
-    if (err_flag) atomicOr_system(err_flag, what);
+    if (err_flag) *(reinterpret_cast<volatile int*>(err_flag) + (what == kIdxSpeaker ? 1 : 0)) = 1;
     return 0;
   }
   return id;

@@ -42,7 +42,7 @@ int set_err(int code, const char* fmt, ...) {
 
 int err_flag_create(ErrFlag* f) {
   DISSC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&f->host), 64, cudaHostAllocMapped));
-  *f->host = 0;
+  f->host[0] = f->host[1] = 0;
   DISSC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&f->dev), f->host, 0));
   return DISSC_OK;
 }
@@ -52,7 +52,8 @@ void err_flag_destroy(ErrFlag* f) {
 }
 int err_flag_take(ErrFlag* f, const char* what, int unit_rows, int spkr_rows) {
   if (!f->host) return DISSC_OK;
-  const int v = __atomic_exchange_n(f->host, 0, __ATOMIC_ACQ_REL);
+  const int v = (__atomic_exchange_n(&f->host[0], 0, __ATOMIC_ACQ_REL) ? kIdxUnit : 0) |
+                (__atomic_exchange_n(&f->host[1], 0, __ATOMIC_ACQ_REL) ? kIdxSpeaker : 0);
   if (!v) return DISSC_OK;
   return set_err(DISSC_EINDEX, "%s: index out of range in self:%s%s%s (unit table has %d rows, speaker table %d)", what,
                  (v & kIdxUnit) ? " unit id" : "", (v & kIdxUnit) && (v & kIdxSpeaker) ? " and" : "",

@@ -16,7 +16,8 @@ bool conv_supported(int k, int dil);
 int launch_conv(const ConvParams& p, int k, int dil, int co_tile, bool emb, cudaStream_t st);
 
 
-// Per-handle error flag for out-of-range embedding ids (common.cuh::checked_row): one int in mapped pinned host memory.
+// Per-handle error flags for out-of-range embedding ids (common.cuh::checked_row): two ints ([0] unit ids, [1] speaker
+// ids) in mapped pinned host memory.
 struct ErrFlag {
   int* host = nullptr;  // read by the host after a synchronisation
   int* dev = nullptr;   // the same word as seen from the device
