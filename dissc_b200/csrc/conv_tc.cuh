@@ -93,7 +93,6 @@ struct TcParams {
   // would otherwise underflow / saturate).  The INPUT planes hold value * in_scale: the host folds 1 / in_scale into
   // w_inv_scale.  The OUTPUT planes are written as act(value) * plane_scale.  0 means 1.
   float in_scale, plane_scale;
-  int exp_half_w;        // EXPERIMENT ONLY (DISSC_EXP_HALFW=1, wrong results): stream half of every weight stage's bytes
   // 2-CTA clusters sharing ONE weight stream (EPW == 8, streamed weights): the two CTAs of a cluster work on two
   // different tiles of the same N chunk in lockstep; each loads half of every weight stage and multicasts it into both
   // CTAs' shared memory, which halves the L2 -> SM weight traffic (43 B/clk/SM without it, the chip's L2 limit).
@@ -352,7 +351,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
               const int nt = min(p.JG, p.k - j0);
               const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
               if (!p.resident) mbar_wait(&w_empty[slot], wph ^ 1);
-              const uint32_t wbytes = ((uint32_t)nt * w_tap_bytes) >> p.exp_half_w;
+              const uint32_t wbytes = (uint32_t)nt * w_tap_bytes;
               mbar_arrive_expect_tx(&w_full[slot], wbytes);
               const unsigned char* wsrc = wchunk + ((size_t)cb * p.k + j0) * w_tap_bytes;
               if (cl2) {

@@ -424,14 +424,6 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   p.resident = L.resident; p.tmem_cols = L.tmem_cols; p.acc_cols = L.acc_cols; p.nbuf = L.nbuf; p.NA = L.NA;
   if (p.in_scale == 0.f) p.in_scale = 1.f;
   if (p.plane_scale == 0.f) p.plane_scale = 1.f;
-  {
-    static int half_w = -1;   // experiment switch, see TcParams::exp_half_w
-    if (half_w < 0) {
-      const char* e = getenv("DISSC_EXP_HALFW");
-      half_w = e ? atoi(e) : 0;
-    }
-    p.exp_half_w = (!L.resident && half_w > 0) ? half_w : 0;
-  }
   p.single_acc = L.single_acc; p.w = L.w; p.w_inv_scale = L.inv_scale / p.in_scale;   // powers of two: exact
   p.Cin8 = L.cin8_total ? L.cin8_total : L.Cin_pad / 8; p.Cout = L.Cout; p.n_chunks = L.n_chunks;
   p.up = L.up; p.up_P = L.up_P; p.up_pad = L.up_pad;
@@ -456,7 +448,7 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   }
   const bool epw8 = L.NC >= 128 || (L.NC == 64 && L.ctas_per_sm == 1 && g_tc_epw64 == 8 && mode != kTcGeneric);
   p.cluster2 = 0;
-  if (g_tc_cluster2 && epw8 && !L.resident && L.split_w && L.ctas_per_sm == 1 && p.n_tiles >= 2 && !p.exp_half_w) {
+  if (g_tc_cluster2 && epw8 && !L.resident && L.split_w && L.ctas_per_sm == 1 && p.n_tiles >= 2) {
     const int pair_items = ((p.n_tiles + 1) / 2) * L.n_chunks;
     grid = std::min(2 * pair_items, num_sms()) & ~1;
     p.cluster2 = grid >= 2 ? 1 : 0;

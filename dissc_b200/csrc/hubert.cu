@@ -663,6 +663,101 @@ __global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, co
   }
 }
 
+// Tiled form of the same assignment (round 2): a CTA takes 32 frames of one clip and ALL centroids, so every centroid
+// value is read from L2 once per CTA instead of once per warp.  256 threads = 16 frame pairs x 16 centroid lanes; a
+// thread accumulates the squared distances of its 2 frames to centroids cg, cg + 16, ..., cg + 112 over 32-channel
+// chunks staged in shared memory (x chunk [4 c8][32 t][8], centroid chunk [8 quads][128 j][4]: conflict-free /
+// broadcast LDS.128).  Distances are summed per chunk and then across chunks (two-level fp32 sum), the argmin runs
+// over (distance, index) pairs -- lowest index on ties -- first inside the thread, then across the 16 centroid lanes.
+constexpr int kKmTileT = 32, kKmMaxK = 128, kKmChunk = 32;
+__global__ void __launch_bounds__(256) hub_kmeans_tiled_kernel(const float* x, const float* cent, const int* lengths, int B,
+                                                               int D8, int T, int Tr, int K, long long* units,
+                                                               float* feat_out /* (B,T,D) or null */) {
+  __shared__ __align__(16) float sx[4 * kKmTileT * 8];            // [c8 of the chunk][t][8]
+  __shared__ __align__(16) float sc[8 * kKmMaxK * 4];             // [channel quad of the chunk][j][4]
+  const int tiles_per_b = (T + kKmTileT - 1) / kKmTileT;
+  const int b = blockIdx.x / tiles_per_b, t0 = (blockIdx.x - b * tiles_per_b) * kKmTileT;
+  const int Tv = lengths ? min(T, lengths[b]) : T;
+  const int tid = threadIdx.x, cg = tid & 15, fg = tid >> 4;      // centroid lane, frame pair
+  const int D = D8 * 8;
+  float tot[2][8];
+#pragma unroll
+  for (int f = 0; f < 2; ++f)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot[f][i] = 0.f;
+  for (int d0 = 0; d0 < D; d0 += kKmChunk) {
+    __syncthreads();   // everyone is done with the previous chunk
+    {
+      // x chunk: 4 slabs x 32 rows x 32 bytes; thread = (slab, row): one 32-byte row
+      const int c8 = tid >> 6, r = (tid >> 1) & 31, half = tid & 1;
+      const int t = t0 + r;
+      float4 v = make_float4(0, 0, 0, 0);
+      if (t < Tv) v = *reinterpret_cast<const float4*>(x + (((size_t)b * D8 + d0 / 8 + c8) * Tr + t) * 8 + half * 4);
+      *reinterpret_cast<float4*>(&sx[(c8 * kKmTileT + r) * 8 + half * 4]) = v;
+      if (feat_out && t < T) *reinterpret_cast<float4*>(feat_out + ((size_t)b * T + t) * D + d0 + c8 * 8 + half * 4) = v;
+      // centroid chunk: K rows x 32 channels -> [quad][j][4]
+      for (int i = tid; i < kKmMaxK * 8; i += 256) {
+        const int j = i >> 3, q = i & 7;
+        float4 c = make_float4(0, 0, 0, 0);
+        if (j < K) c = __ldg(reinterpret_cast<const float4*>(cent + (size_t)j * D + d0 + q * 4));
+        *reinterpret_cast<float4*>(&sc[(q * kKmMaxK + j) * 4]) = c;
+      }
+    }
+    __syncthreads();
+    float acc[2][8];
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[f][i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {       // channel quad of the chunk: slab q / 2, half q & 1
+      const float4 x0 = *reinterpret_cast<const float4*>(&sx[((q >> 1) * kKmTileT + 2 * fg) * 8 + (q & 1) * 4]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&sx[((q >> 1) * kKmTileT + 2 * fg + 1) * 8 + (q & 1) * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 c = *reinterpret_cast<const float4*>(&sc[(q * kKmMaxK + cg + 16 * i) * 4]);
+        float u;
+        u = x0.x - c.x; acc[0][i] = fmaf(u, u, acc[0][i]);
+        u = x0.y - c.y; acc[0][i] = fmaf(u, u, acc[0][i]);
+        u = x0.z - c.z; acc[0][i] = fmaf(u, u, acc[0][i]);
+        u = x0.w - c.w; acc[0][i] = fmaf(u, u, acc[0][i]);
+        u = x1.x - c.x; acc[1][i] = fmaf(u, u, acc[1][i]);
+        u = x1.y - c.y; acc[1][i] = fmaf(u, u, acc[1][i]);
+        u = x1.z - c.z; acc[1][i] = fmaf(u, u, acc[1][i]);
+        u = x1.w - c.w; acc[1][i] = fmaf(u, u, acc[1][i]);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tot[f][i] += acc[f][i];
+  }
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    float best = INFINITY;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {       // ascending index inside the thread: strict '<' keeps the lowest on ties
+      const int j = cg + 16 * i;
+      if (j < K && tot[f][i] < best) {
+        best = tot[f][i];
+        besti = j;
+      }
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {  // across the 16 centroid lanes (one half-warp)
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob < best || (ob == best && oi < besti)) {
+        best = ob;
+        besti = oi;
+      }
+    }
+    const int t = t0 + 2 * fg + f;
+    if (cg == 0 && t < T) units[(size_t)b * T + t] = t < Tv ? besti : -1;
+  }
+}
+
 // standalone: x (M, D) row-major
 __global__ void __launch_bounds__(256) kmeans_rowmajor_kernel(const float* x, const float* cent, int M, int D, int K,
                                                               long long* out) {
@@ -1131,9 +1226,14 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     HUB_TRY(hub_layernorm(bf.Y, Ly.ln2_w, Ly.ln2_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
   }
   {
-    const long long threads = (((long long)B * T + kKmFrames - 1) / kKmFrames) * 32;
-    hub_kmeans_f32b_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(bf.H, g->cent, lenT, B, D / 8, T, Tr, c.n_clusters,
-                                                                         reinterpret_cast<long long*>(units), features);
+    if (c.n_clusters <= kKmMaxK && D % kKmChunk == 0) {
+      hub_kmeans_tiled_kernel<<<B * ((T + kKmTileT - 1) / kKmTileT), 256, 0, st>>>(
+          bf.H, g->cent, lenT, B, D / 8, T, Tr, c.n_clusters, reinterpret_cast<long long*>(units), features);
+    } else {
+      const long long threads = (((long long)B * T + kKmFrames - 1) / kKmFrames) * 32;
+      hub_kmeans_f32b_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(bf.H, g->cent, lenT, B, D / 8, T, Tr, c.n_clusters,
+                                                                           reinterpret_cast<long long*>(units), features);
+    }
     DISSC_CUDA(cudaGetLastError());
   }
   if (n_frames) DISSC_CUDA(cudaMemcpyAsync(n_frames, lenT, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
