@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdissc_b200.so")
+# DISSC_LIB selects an A/B build of the same sources (dissc_b200/build.py::build_variant); default: the in-tree library
+LIB_PATH = os.environ.get("DISSC_LIB") or os.path.join(HERE, "libdissc_b200.so")
 
 MAX_STAGES, MAX_KERNELS, MAX_DILATIONS = 8, 8, 8
 

@@ -33,8 +33,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every csrc/*.cu (one nvcc process per file, in parallel) and link the shared library."""
     if not force and not _stale():
         return LIB
+    return _build(LIB, os.path.join(HERE, "build"), [], force, verbose)
+
+
+def build_variant(tag: str, defines, verbose: bool = False) -> str:
+    """A/B builds of compile-time constants: `libdissc_b200_<tag>.so` compiled with extra -D flags, selected at run time with
+    DISSC_LIB=<path> (dissc_b200/_lib.py).  Measurement aid only."""
+    out = os.path.join(HERE, f"libdissc_b200_{tag}.so")
+    return _build(out, os.path.join(HERE, f"build_{tag}"), [f"-D{d}" for d in defines], True, verbose)
+
+
+def _build(LIB: str, objdir: str, extra, force: bool, verbose: bool) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
     hdr_t = max([os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))
@@ -44,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if not force and os.path.isfile(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
             continue
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd)))

@@ -50,7 +50,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires)
 // instead of re-issuing the try_wait / branch pair every ~60 cycles -- ncu counted 46 M such spin iterations per launch of
 // the C = 64 pair kernel (40 % of all issued instructions), pure power on a power-capped part.
-constexpr uint32_t kMbarSuspendNs = 2000;
+#ifndef DISSC_MBAR_SUSPEND_NS
+#define DISSC_MBAR_SUSPEND_NS 2000
+#endif
+constexpr uint32_t kMbarSuspendNs = DISSC_MBAR_SUSPEND_NS;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
