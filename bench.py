@@ -142,9 +142,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2..4] sub-records")
     ap.add_argument("--settle", type=float, default=1.5,
-                    help="seconds of untimed back-to-back forwards before the first timed region (on top of --warmup): "
-                         "under its power cap the chip's clock keeps sinking for the first second or two of sustained "
-                         "load, so without this the phase measured first (value) looks ~2%% faster than the later ones")
+                    help="seconds of untimed back-to-back forwards before the extra `sustained` leg: under its power cap "
+                         "the chip's clock keeps sinking for the first seconds of continuous load, so the legs measured "
+                         "later (e2e, gathered, sustained) run 2-6%% below the one measured first (value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -194,11 +194,6 @@ def main():
     for _ in range(args.warmup):
         y = gen(code=code, f0=f0, spkr=spkr)
     torch.cuda.synchronize()
-    t_settle = time.perf_counter()
-    while time.perf_counter() - t_settle < args.settle:
-        for _ in range(5):
-            y = gen(code=code, f0=f0, spkr=spkr)
-        torch.cuda.synchronize()
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -285,6 +280,32 @@ def main():
             want_l = gen.generate_int16(cg[-B:].to(dev), fg[-B:].reshape(B, T).to(dev), sg[-B:].reshape(B).to(dev),
                                         lengths=lg[-B:].to(dev))
             gathered["bit_identical_last_rank"] = bool(torch.equal(pipe.gathered[last][world - 1], want_l))
+
+    # ---- the same device-resident leg again after --settle seconds of continuous load (steady thermal / power state) --
+    sustained = None
+    if args.settle > 0:
+        t_settle = time.perf_counter()
+        while time.perf_counter() - t_settle < args.settle:
+            for _ in range(5):
+                y = gen(code=code, f0=f0, spkr=spkr)
+            torch.cuda.synchronize()
+        sampler2 = ClockSampler(local)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        sampler2.start()
+        s0.record()
+        for _ in range(args.steps):
+            y = gen(code=code, f0=f0, spkr=spkr)
+        s1.record()
+        torch.cuda.synchronize()
+        clocks2 = sampler2.stop()
+        barrier()
+        ms_sus = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+        sustained = {"value": world * n_samples / (ms_sus * 1e-3), "unit": UNIT, "ms_per_step": ms_sus,
+                     "sm_mhz": clocks2.get("sm_mhz"),
+                     "note": f"the `value` leg repeated after {args.settle:g} s more of back-to-back forwards on top of the "
+                             "e2e and gathered legs: the power-capped clock has settled"}
 
     # ---- BASELINE configs[2..4]: short, bounded runs of the other configs on this rank's shard ---------------------
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
@@ -382,6 +403,7 @@ def main():
                        "every step does H2D + forward + D2H, a step's D2H overlaps the next step's forward)",
                 "bit_identical_to_device_path": parity_e2e},
         "gathered": gathered,
+        "sustained": sustained,
         "gpu_launches": gen.launches_per_forward() * args.steps,
         "roofline": {"bound": "tensor", "achieved": split_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": split_tflops / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
