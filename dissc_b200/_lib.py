@@ -52,6 +52,7 @@ EXPORTS = [
     "dissc_hubert_create", "dissc_hubert_destroy", "dissc_hubert_num_frames", "dissc_hubert_workspace_bytes",
     "dissc_hubert_forward", "dissc_kmeans_assign", "dissc_gen_status", "dissc_pred_status",
     "dissc_gen_forward_host_submit", "dissc_gen_forward_host_wait", "dissc_gen_host_reserve",
+    "dissc_gen_forward_ex", "dissc_gen_n_extra",
 ]
 
 
@@ -111,6 +112,9 @@ def lib():
                                                 c_void_p, c_void_p]
     L.dissc_gen_forward_host_wait.argtypes = [c_void_p, c_int]
     L.dissc_gen_host_reserve.argtypes = [c_void_p, c_int, c_int]
+    L.dissc_gen_forward_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_size_t, c_void_p]
+    L.dissc_gen_n_extra.argtypes = [c_void_p]
     L.dissc_gen_status.argtypes = [c_void_p]
     L.dissc_pred_status.argtypes = [c_void_p]
     L.dissc_len_carryover.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]

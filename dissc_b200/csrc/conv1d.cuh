@@ -32,6 +32,8 @@ struct ConvParams {
   const float* dict_w;    // (num_embeddings, E)
   const float* spkr_w;    // (rows, E)
   int E, f0_ch, spk_base; // f0_ch = -1 if absent; spk_base = first speaker channel or -1
+  const float* extra;     // (B, n_extra) or null: per-utterance conditioning features, channels [extra_base, +n_extra)
+  int extra_base, n_extra;
   int n_code_rows, n_spkr_rows;  // table rows: ids outside [0, rows) set *err (common.cuh::checked_row)
   int* err;
 
@@ -111,6 +113,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_fused_kernel(const ConvPar
               v = __ldg(p.dict_w + (size_t)checked_row(p.code[(size_t)b * p.T + t], p.n_code_rows, p.err, kIdxUnit) * p.E + ci);
             } else if (ci == p.f0_ch) {
               v = __ldg(p.f0 + (size_t)b * p.T + t);
+            } else if (p.n_extra > 0 && ci >= p.extra_base) {
+              v = __ldg(p.extra + (size_t)b * p.n_extra + (ci - p.extra_base));
             } else {
               v = __ldg(p.spkr_w + (size_t)checked_row(p.spkr[b], p.n_spkr_rows, p.err, kIdxSpeaker) * p.E + (ci - p.spk_base));
             }

@@ -618,6 +618,8 @@ struct EmbedParams {
   const float* spkr_w;    // (rows, E)
   const int* lengths;
   int E, f0_ch, spk_base, Cin;  // f0_ch / spk_base = -1 if absent
+  const float* extra;     // (B, n_extra) or null: per-utterance conditioning features repeated over time as channels
+  int extra_base, n_extra;  //   [extra_base, extra_base + n_extra) (sr/models.py:216-221, e.g. `f0_stats`)
   int B, C8, T, Tp;
   float scale;                   // planes hold value * scale (TcParams::in_scale of conv_pre)
   int n_code_rows, n_spkr_rows;  // table rows: ids outside [0, rows) set *err (common.cuh::checked_row)
@@ -643,6 +645,8 @@ static __global__ void tc_embed_planes_kernel(const EmbedParams p) {
           x = __ldg(p.dict_w + (size_t)checked_row(p.code[(size_t)b * p.T + t], p.n_code_rows, p.err, kIdxUnit) * p.E + ci);
         } else if (ci == p.f0_ch) {
           x = __ldg(p.f0 + (size_t)b * p.T + t);
+        } else if (p.n_extra > 0 && ci >= p.extra_base) {
+          x = __ldg(p.extra + (size_t)b * p.n_extra + (ci - p.extra_base));
         } else if (p.spk_base >= 0 && ci >= p.spk_base) {
           x = __ldg(p.spkr_w + (size_t)checked_row(p.spkr[b], p.n_spkr_rows, p.err, kIdxSpeaker) * p.E + (ci - p.spk_base));
         }

@@ -755,6 +755,7 @@ struct dissc_gen {
   float* dict_w = nullptr;
   float* spkr_w = nullptr;
   int n_launches = 0;
+  int n_extra = 0;     // per-utterance conditioning channels after the speaker embedding (model_in_dim - the three standard parts)
   dissc::ErrFlag err;  // out-of-range unit / speaker ids (dissc_gen_status)
   // power-of-two activation scales of the split-fp16 planes (estimate_act_scales): embedding planes, conv_pre output,
   // per stage the residual stream x (x_up and every r) and the stage output, per conv pair the intermediate xt
@@ -903,7 +904,10 @@ static void estimate_act_scales(dissc_gen* g, const WeightMap& wm) {
   constexpr double kLrelu = 0.505;   // E[lrelu(x, 0.1)^2] / E[x^2] for a symmetric x
   const double ms_dict = mean_sq(wm.get("dict.weight")), ms_spk = c.has_spkr ? mean_sq(wm.get("spkr.weight")) : 0.0;
   const double ms_f0 = c.has_f0 ? 1.0 : 0.0;   // speaker-normalised F0, sr/dataset.py:297-312
-  g->s_emb = pow2_scale_for_rms(std::sqrt(std::max(ms_dict, std::max(ms_spk, ms_f0))));
+  // extra conditioning channels (`f0_stats`: a speaker's F0 mean / std in Hz, ~1e2) share the embedding planes: leave
+  // them 2^7 of headroom on top of the table values
+  const double ms_extra = g->n_extra > 0 ? 128.0 * 128.0 : 0.0;
+  g->s_emb = pow2_scale_for_rms(std::sqrt(std::max(std::max(ms_dict, ms_extra), std::max(ms_spk, ms_f0))));
   double ms = (c.embedding_dim * ms_dict + ms_f0 + (c.has_spkr ? c.embedding_dim * ms_spk : 0.0)) / std::max(1, c.model_in_dim);
   double gain, b2;
   conv_moments(wm, "conv_pre", c.c0, 1, &gain, &b2);
@@ -1000,8 +1004,11 @@ struct Launcher {
 
 static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, const int64_t* spkr,
                         const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16, void* workspace,
-                        size_t workspace_bytes, cudaStream_t st, Profiler* prof) {
+                        size_t workspace_bytes, cudaStream_t st, Profiler* prof, const float* extra = nullptr) {
   DISSC_CHECK(g && code && (out_f32 || out_i16), DISSC_EINVAL, "null handle / code / out");
+  DISSC_CHECK(g->n_extra == 0 || extra, DISSC_EINVAL,
+              "the config has %d extra conditioning channels (model_in_dim %d): use dissc_gen_forward_ex with `extra`",
+              g->n_extra, g->cfg.model_in_dim);
   DISSC_CHECK(B > 0 && T > 0, DISSC_EINVAL, "B=%d T=%d must be positive", B, T);
   DISSC_CHECK(!g->cfg.has_f0 || f0, DISSC_EINVAL, "config has f0 but f0 == NULL");
   DISSC_CHECK(!g->cfg.has_spkr || spkr, DISSC_EINVAL, "config is multi-speaker but spkr == NULL");
@@ -1048,6 +1055,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     e.E = c.embedding_dim; e.f0_ch = c.has_f0 ? c.embedding_dim : -1;
     e.spk_base = c.has_spkr ? c.embedding_dim + (c.has_f0 ? 1 : 0) : -1;
     e.Cin = c.model_in_dim; e.B = B; e.C8 = g->pre_tc.Cin_pad / 8; e.T = T; e.Tp = Tp0;
+    e.extra = extra; e.n_extra = g->n_extra; e.extra_base = c.model_in_dim - g->n_extra;
     e.hi = P_emb.hi; e.lo = P_emb.lo; e.scale = g->s_emb;
     e.n_code_rows = c.num_embeddings; e.n_spkr_rows = c.n_spkr_rows; e.err = g->err.dev;
     DISSC_TRY(L.begin("embed", 0));
@@ -1080,6 +1088,7 @@ static int forward_impl(dissc_gen* g, const int64_t* code, const float* f0, cons
     p.f0_ch = c.has_f0 ? c.embedding_dim : -1;
     p.spk_base = c.has_spkr ? c.embedding_dim + (c.has_f0 ? 1 : 0) : -1;
     p.n_code_rows = c.num_embeddings; p.n_spkr_rows = c.n_spkr_rows; p.err = g->err.dev;
+    p.extra = extra; p.n_extra = g->n_extra; p.extra_base = c.model_in_dim - g->n_extra;
     p.w = g->pre.w; p.bias = g->pre.bias; p.out = act[0];
     p.lengths = lengths; p.len_mul = 1;
     p.B = B; p.Cin = g->pre.Cin; p.Cout = g->pre.Cout; p.T = T; p.pad = g->pre.pad;
@@ -1470,10 +1479,8 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
               DISSC_EINVAL, "bad stage/kernel counts");
   DISSC_CHECK(c.resblock == 1 || c.resblock == 2, DISSC_EUNSUPPORTED, "resblock must be \"1\" or \"2\"");
   const int expect_in = c.embedding_dim + (c.has_f0 ? 1 : 0) + (c.has_spkr ? c.embedding_dim : 0);
-  DISSC_CHECK(c.model_in_dim == expect_in, DISSC_EUNSUPPORTED,
-              "model_in_dim=%d but embedding_dim/f0/multispkr give %d channels (extra conditioning features such as "
-              "f0_stats are not supported)",
-              c.model_in_dim, expect_in);
+  DISSC_CHECK(c.model_in_dim >= expect_in, DISSC_EUNSUPPORTED,
+              "model_in_dim=%d but embedding_dim/f0/multispkr alone give %d channels", c.model_in_dim, expect_in);
   struct DeviceGuard {   // the caller's current device is restored on every exit path
     int prev = -1;
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
@@ -1486,6 +1493,7 @@ int dissc_gen_create(dissc_gen_t** out, const dissc_gen_cfg* cfg, const dissc_te
   dissc_gen* g = new dissc_gen();
   g->cfg = c;
   g->device = device;
+  g->n_extra = c.model_in_dim - expect_in;   // e.g. 2 for `f0_feats` (the f0_stats mean / std channels, sr/models.py:216-221)
   auto fail = [&](int rc) {
     dissc_gen_destroy(g);
     return rc;
@@ -1722,6 +1730,16 @@ int dissc_gen_host_reserve(dissc_gen_t* g, int B, int T) {
   DISSC_TRY(host_streams(g));
   return host_arena_reserve(g, B, T);
 }
+
+int dissc_gen_forward_ex(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr, const float* extra,
+                         const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  DISSC_CHECK((out_f32 != nullptr) != (out_i16 != nullptr), DISSC_EINVAL, "exactly one of out_f32 / out_i16");
+  return forward_impl(g, code, f0, spkr, lengths, B, T, out_f32, out_i16, workspace, workspace_bytes,
+                      static_cast<cudaStream_t>(stream), nullptr, extra);
+}
+
+int dissc_gen_n_extra(const dissc_gen_t* g) { return g ? g->n_extra : 0; }
 
 int dissc_gen_forward_host_submit(dissc_gen_t* g, int slot, const int64_t* code, const float* f0, const int64_t* spkr,
                                   const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16) {

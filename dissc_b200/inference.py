@@ -80,10 +80,15 @@ def parse_speaker(path, method) -> str:
     raise NotImplementedError(method)
 
 
-def normalize_f0(f0: np.ndarray, mean: float, std: float) -> np.ndarray:
-    """sr/dataset.py:306-312 (no f0_median): voiced frames (f0 != 0) -> (f0 - mean) / std; unvoiced stay 0."""
+def normalize_f0(f0: np.ndarray, mean: float, std: float, f0_median: bool = False) -> np.ndarray:
+    """sr/dataset.py:297-312: voiced frames (f0 != 0) -> (f0 - mean) / std; unvoiced frames stay 0, or with
+    ``f0_median`` are filled with the utterance's voiced median first and normalised like the rest (:306-309)."""
     f0 = f0.astype(np.float32).copy()
     ii = f0 != 0
+    if f0_median:
+        med = np.median(f0[ii])          # NaN (with numpy's warning) for an all-unvoiced utterance, as in the reference
+        f0[~ii] = med
+        f0[~ii] = (f0[~ii] - mean) / std
     f0[ii] = (f0[ii] - mean) / std
     return f0
 
@@ -91,8 +96,6 @@ def normalize_f0(f0: np.ndarray, mean: float, std: float) -> np.ndarray:
 def prepare_items(h, audio_files, codes, pitch, id_to_spkr: Sequence[str], f0_stats: Optional[dict],
                   unseen_speaker: bool = False) -> List[dict]:
     """The slice of CodeDataset.__getitem__ (sr/dataset.py:221-317) that feeds the Generator at inference."""
-    if h.get("f0_median", False) or h.get("f0_feats", False):
-        raise NotImplementedError("f0_median / f0_feats configs are not supported")
     spkr_to_id = {k: v for v, k in enumerate(id_to_spkr)}
     items = []
     for i, (path, code) in enumerate(zip(audio_files, codes)):
@@ -105,7 +108,9 @@ def prepare_items(h, audio_files, codes, pitch, id_to_spkr: Sequence[str], f0_st
                 name = parse_speaker(path, h.get("multispkr", None))
                 st = f0_stats if name not in f0_stats else f0_stats[name]
                 mean, std = (st["f0_mean"], st["f0_std"]) if name not in f0_stats else (st["mean"], st["std"])
-                f0 = normalize_f0(f0, mean, std)
+                f0 = normalize_f0(f0, mean, std, bool(h.get("f0_median", False)))
+                if h.get("f0_feats", False):           # sr/dataset.py:314-315: the source speaker's [mean, std]
+                    it["f0_stats"] = np.asarray([mean, std], dtype=np.float32)
             it["f0"] = f0
             n = min(len(it["code"]), len(f0))
             if len(it["code"]) != len(f0):
@@ -183,8 +188,11 @@ def batches_by_length(lengths: Sequence[int], max_batch: int, max_frames: int) -
 
 @torch.no_grad()
 def vocode_items(generator: CodeGenerator, items: List[dict], device, spkr_override: Optional[int] = None,
-                 max_batch: int = 64, max_frames: int = 64 * 400) -> Dict[int, np.ndarray]:
-    """-> {item index: int16 waveform (hop * n_frames,)}, identical per item to ``generate()`` (sr/inference.py:67-76)."""
+                 max_batch: int = 64, max_frames: int = 64 * 400,
+                 f0_stats_override: Optional[Sequence[float]] = None) -> Dict[int, np.ndarray]:
+    """-> {item index: int16 waveform (hop * n_frames,)}, identical per item to ``generate()`` (sr/inference.py:67-76).
+    Items carrying ``f0_stats`` (``f0_feats`` configs) pass it on as the extra conditioning feature; ``f0_stats_override``
+    replaces it with the TARGET speaker's [mean, std] for voice conversion (sr/inference.py:237-245)."""
     hop = generator.hop
     out: Dict[int, np.ndarray] = {}
     n_frames = []
@@ -200,6 +208,11 @@ def vocode_items(generator: CodeGenerator, items: List[dict], device, spkr_overr
         f0 = torch.zeros((B, T), dtype=torch.float32)
         spkr = torch.zeros((B, 1), dtype=torch.int64)
         lengths = torch.zeros((B,), dtype=torch.int32)
+        feats = {}
+        if any("f0_stats" in items[i] for i in idx) or f0_stats_override is not None:
+            st = [np.asarray(f0_stats_override if f0_stats_override is not None else items[i]["f0_stats"], dtype=np.float32)
+                  for i in idx]
+            feats["f0_stats"] = torch.from_numpy(np.stack(st)).to(device)
         for b, i in enumerate(idx):
             it = items[i]
             n = n_frames[i]
@@ -215,7 +228,7 @@ def vocode_items(generator: CodeGenerator, items: List[dict], device, spkr_overr
             spkr[b, 0] = it.get("spkr", 0) if spkr_override is None else spkr_override
             lengths[b] = n
         y = generator.generate_int16(code.to(device), f0.to(device) if generator.f0 else None,
-                                     spkr.to(device) if generator.multispkr else None, lengths=lengths.to(device))
+                                     spkr.to(device) if generator.multispkr else None, lengths=lengths.to(device), **feats)
         y = y.cpu().numpy()
         generator.check_indices(synchronize=False)   # the .cpu() above synchronised: bad unit / speaker ids raise here
         for b, i in enumerate(idx):
@@ -435,6 +448,7 @@ def main(argv: Optional[Sequence[str]] = None):
         if a.f0_stats and h.get("f0", None) is not None:
             f0_tgt = _torch_load(a.f0_stats)                   # sr/inference.py:157-158
         rescale = f0_tgt is not None and not h.get("f0_normalize", False)
+        feats_stats = None
         order: List[int] = []
         for ks in per_item:
             for k in ks:
@@ -449,7 +463,12 @@ def main(argv: Optional[Sequence[str]] = None):
                     if (my_items[j]["f0"] != 0).any():
                         my_items[j]["f0"] = rescale_f0(my_items[j]["f0"], *target_f0_stats(f0_tgt, k))
             sub = [my_items[j] for j in sel]
-            for i, audio in vocode_items(generator, sub, device, k, a.batch).items():
+            tgt_stats = None
+            if h.get("f0_feats", False):                       # sr/inference.py:237-245: the TARGET speaker's [mean, std]
+                if feats_stats is None:
+                    feats_stats = _torch_load(h["f0_stats"])
+                tgt_stats = list(target_f0_stats(feats_stats, k))
+            for i, audio in vocode_items(generator, sub, device, k, a.batch, f0_stats_override=tgt_stats).items():
                 writer.submit(os.path.join(a.output_dir, out_name(sub[i]) + f"_{k}_gen.wav"), h.sampling_rate, audio)
     if write_gt:
         for it, gt in zip(my_items, gts):

@@ -96,8 +96,6 @@ class CodeGenerator(nn.Module):
             if get(key, None):
                 raise NotImplementedError(
                     f"config key '{key}' selects a VQ branch of sr/models.py:137-156 that dissc_b200 does not implement")
-        if get("f0_feats", False):
-            raise NotImplementedError("f0_feats (extra f0_stats conditioning channels, sr/models.py:216-221) unsupported")
         self.resblock = str(h["resblock"])
         self.rates = list(h["upsample_rates"])
         self.up_kernels = list(h["upsample_kernel_sizes"])
@@ -145,11 +143,30 @@ class CodeGenerator(nn.Module):
         self._drop_handle()
         return super()._apply(fn, *a, **kw)
 
+    def _extra_channels(self, kwargs, B):
+        """Every keyword argument other than code / f0 / spkr is a conditioning feature appended as channels, in
+        keyword order, after nearest-repeat upsampling over time (sr/models.py:216-221; `f0_feats` configs pass
+        `f0_stats` = [mean, std] per utterance, sr/inference.py:237-245).  Supported: features that are constant over
+        time, i.e. (B, n) or (B, n, 1) -> (B, n_extra) fp32; model_in_dim must account for them."""
+        feats = []
+        for k, v in kwargs.items():
+            if k in ("code", "f0", "spkr"):
+                continue
+            if v.dim() == 3 and v.shape[-1] == 1:
+                v = v[..., 0]
+            if v.dim() != 2 or v.shape[0] != B:
+                raise NotImplementedError(f"conditioning feature '{k}' of shape {tuple(v.shape)}: only per-utterance "
+                                          "features (B, n) / (B, n, 1) are supported (sr/models.py:216-221)")
+            feats.append(v.to(torch.float32))
+        n_extra = self.in_dim - self.emb_dim - (1 if self.f0 else 0) - (self.emb_dim if self.multispkr else 0)
+        got = sum(f.shape[1] for f in feats)
+        if got != n_extra:
+            raise ValueError(f"model_in_dim={self.in_dim} leaves {n_extra} extra conditioning channel(s), got {got} "
+                             f"({[k for k in kwargs if k not in ('code', 'f0', 'spkr')]})")
+        return torch.cat(feats, dim=1).contiguous() if feats else None
+
     def forward(self, **kwargs):
         lengths = kwargs.pop("lengths", None)  # extension: per-utterance valid frames (varlen batches)
-        extra = [k for k in kwargs if k not in ("code", "f0", "spkr")]
-        if extra:
-            raise NotImplementedError(f"extra conditioning features {extra} (sr/models.py:216-221) are not supported")
         code = kwargs["code"]
         if not code.is_cuda:
             raise _lib.DisscError("dissc_b200.CodeGenerator runs only on CUDA (sm_100a); there is no CPU path")
@@ -181,9 +198,10 @@ class CodeGenerator(nn.Module):
             spkr = spkr.reshape(B).to(torch.int64).contiguous()
         if lengths is not None:
             lengths = lengths.to(device=code.device, dtype=torch.int32).contiguous()
-        return self._run(code, f0, spkr, lengths, B, T, out_dtype=torch.float32).view(B, 1, -1)
+        extra = self._extra_channels(kwargs, B)
+        return self._run(code, f0, spkr, lengths, B, T, out_dtype=torch.float32, extra=extra).view(B, 1, -1)
 
-    def generate_int16(self, code, f0=None, spkr=None, lengths=None, out=None):
+    def generate_int16(self, code, f0=None, spkr=None, lengths=None, out=None, **features):
         """Fused ``generate()`` of sr/inference.py:67-76: returns int16 (B, hop*T) on the device.  ``out``: an existing
         contiguous int16 (B, hop*T) device tensor the last kernel writes into directly (e.g. the send buffer of a
         gather, ``dist.ScatterGatherPipeline``)."""
@@ -192,7 +210,8 @@ class CodeGenerator(nn.Module):
         spkr = None if spkr is None else spkr.reshape(B).to(torch.int64).contiguous()
         if lengths is not None:
             lengths = lengths.to(device=code.device, dtype=torch.int32).contiguous()
-        return self._run(code.contiguous(), f0, spkr, lengths, B, T, out_dtype=torch.int16, out=out)
+        extra = self._extra_channels(features, B)
+        return self._run(code.contiguous(), f0, spkr, lengths, B, T, out_dtype=torch.int16, out=out, extra=extra)
 
     # ---- C-ABI plumbing ------------------------------------------------------
     def folded_state_dict(self):
@@ -276,7 +295,7 @@ class CodeGenerator(nn.Module):
         _lib.check(_lib.lib().dissc_gen_workspace_bytes(self._ensure_handle(device), B, T, ctypes.byref(n)))
         return n.value
 
-    def _run(self, code, f0, spkr, lengths, B, T, out_dtype, ws=None, out=None):
+    def _run(self, code, f0, spkr, lengths, B, T, out_dtype, ws=None, out=None, extra=None):
         dev = code.device
         L = _lib.lib()
         h = self._ensure_handle(dev)
@@ -296,9 +315,16 @@ class CodeGenerator(nn.Module):
         ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            fn = L.dissc_gen_forward if out_dtype == torch.float32 else L.dissc_gen_forward_i16
-            _lib.check(fn(h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T, ptr(out), ptr(ws), ws.numel(), stream),
-                       "dissc_gen_forward")
+            if extra is not None:
+                f32 = out_dtype == torch.float32
+                extra = extra.to(device=dev, dtype=torch.float32).contiguous()
+                _lib.check(L.dissc_gen_forward_ex(h, ptr(code), ptr(f0), ptr(spkr), ptr(extra), ptr(lengths), B, T,
+                                                  ptr(out) if f32 else None, None if f32 else ptr(out), ptr(ws), ws.numel(),
+                                                  stream), "dissc_gen_forward_ex")
+            else:
+                fn = L.dissc_gen_forward if f32_out(out_dtype) else L.dissc_gen_forward_i16
+                _lib.check(fn(h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T, ptr(out), ptr(ws), ws.numel(), stream),
+                           "dissc_gen_forward")
         return out
 
     def capture_graph(self, B: int, T: int, device, int16: bool = False, varlen: bool = False):
@@ -415,6 +441,10 @@ class CodeGenerator(nn.Module):
             _lib.check(L.dissc_gen_profile(h, ptr(code), ptr(f0), ptr(spkr), ptr(lengths), B, T, ptr(out), ptr(ws),
                                            need, names, ms, fl, by, cap, ctypes.byref(n)), "dissc_gen_profile")
         return [(names[i].value.decode(), ms[i], fl[i], by[i]) for i in range(n.value)]
+
+
+def f32_out(dtype) -> bool:
+    return dtype == torch.float32
 
 
 class GraphedForward:

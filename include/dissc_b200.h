@@ -112,6 +112,16 @@ int dissc_gen_forward_i16(dissc_gen_t* g, const int64_t* code, const float* f0, 
                           const int32_t* lengths, int B, int T, int16_t* out_i16, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* The same forward for configs with EXTRA conditioning features (`f0_feats`: CodeGenerator.forward appends every
+ * other keyword argument as channels repeated over time, sr/models.py:216-221; sr/inference.py:237-245 passes
+ * `f0_stats` = the target speaker's [mean, std]).  `extra` fp32 (B, n_extra) on the device, n_extra = model_in_dim -
+ * embedding_dim - has_f0 - has_spkr * embedding_dim = dissc_gen_n_extra(g); channel order = order of the columns.
+ * Exactly one of out_f32 / out_i16 is non-NULL.  dissc_gen_forward / _i16 / _host reject handles with n_extra > 0. */
+int dissc_gen_forward_ex(dissc_gen_t* g, const int64_t* code, const float* f0, const int64_t* spkr, const float* extra,
+                         const int32_t* lengths, int B, int T, float* out_f32, int16_t* out_i16, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int dissc_gen_n_extra(const dissc_gen_t* g);
+
 /* End-to-end call with HOST buffers (what sr/inference.py:178 + :69 + :75 do per
  * utterance, batched): H2D of the inputs, forward, D2H of the waveform, stream
  * synchronise.  Pinned host memory makes the copies asynchronous; pageable

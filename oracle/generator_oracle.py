@@ -122,9 +122,10 @@ def generator_forward(sd: dict, h: dict, x: torch.Tensor, return_intermediates: 
 
 
 def build_input(sd: dict, h: dict, code: torch.Tensor, f0: torch.Tensor | None,
-                spkr: torch.Tensor | None) -> torch.Tensor:
-    """sr/models.py:189, :206-215 -- the live branch for the shipped configs
-    (no code_vq / f0 vq / f0 quantizer)."""
+                spkr: torch.Tensor | None, **feats) -> torch.Tensor:
+    """sr/models.py:189, :206-221 -- the live branch for the shipped configs
+    (no code_vq / f0 vq / f0 quantizer); ``feats`` = any further keyword arguments of
+    ``CodeGenerator.forward`` (e.g. ``f0_stats`` for ``f0_feats`` configs)."""
     x = F.embedding(code, sd["dict.weight"]).transpose(1, 2)                       # :189
     if h.get("f0", None):
         if x.shape[-1] < f0.shape[-1]:                                             # :207-210
@@ -136,19 +137,22 @@ def build_input(sd: dict, h: dict, code: torch.Tensor, f0: torch.Tensor | None,
         s = F.embedding(spkr, sd["spkr.weight"]).transpose(1, 2)                   # :213
         s = _upsample(s, x.shape[-1])                                              # :214
         x = torch.cat([x, s], dim=1)                                               # :215
+    for k, feat in feats.items():                                                  # :216-221
+        feat = _upsample(feat.to(x.dtype), x.shape[-1])
+        x = torch.cat([x, feat], dim=1)
     return x
 
 
 @torch.no_grad()
 def code_generator_forward(sd: dict, h: dict, code, f0=None, spkr=None, dtype=torch.float32,
-                           return_intermediates: bool = False):
+                           return_intermediates: bool = False, **feats):
     """CodeGenerator.forward (sr/models.py:179-225) for the shipped configs.
     ``sd`` is a checkpoint-format (weight_g/weight_v) or folded state dict."""
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     if any(k.endswith(".weight_g") for k in sd):
         sd = folded_state_dict(sd)
     f0 = None if f0 is None else f0.to(dtype)
-    x = build_input(sd, h, code, f0, spkr)
+    x = build_input(sd, h, code, f0, spkr, **feats)
     return generator_forward(sd, h, x, return_intermediates)
 
 

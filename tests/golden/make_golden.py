@@ -43,6 +43,29 @@ def gen_tiny():
     print("gen_tiny", y.shape, float(y.std()))
 
 
+def gen_f0feats():
+    """`f0_feats` config: CodeGenerator.forward appends the extra `f0_stats` keyword (B, 2) as two channels
+    (sr/models.py:216-221; sr/inference.py:237-245 passes the target speaker's [mean, std] in Hz)."""
+    cfg = dict(TINY_CONFIG, model_in_dim=TINY_CONFIG["model_in_dim"] + 2, f0_feats=True)
+    sd = syn.synthetic_generator_state_dict(cfg, seed=17)
+    # a trained model's weights on the two Hz-valued channels are small; keep their contribution O(1) so tanh does not saturate
+    sd["conv_pre.weight_v"][:, -2:, :] *= 0.004
+    code, f0, spkr = syn.synthetic_inputs(3, 29, seed=19)
+    g = torch.Generator().manual_seed(23)
+    f0_stats = torch.stack([150 + 60 * torch.rand(3, generator=g), 20 + 15 * torch.rand(3, generator=g)], dim=1)
+    models, AttrDict = _refimport.sr_models()
+    m = models.CodeGenerator(AttrDict(cfg))
+    m.load_state_dict(sd)
+    m.eval()
+    m.remove_weight_norm()
+    with torch.no_grad():
+        y = m(code=code, f0=f0, spkr=spkr, f0_stats=f0_stats)
+    out = {"sd." + k: v.numpy() for k, v in sd.items()}
+    out.update(code=code.numpy(), f0=f0.numpy(), spkr=spkr.numpy(), f0_stats=f0_stats.numpy(), y=y.numpy())
+    np.savez_compressed(os.path.join(HERE, "gen_f0feats.npz"), **out)
+    print("gen_f0feats", y.shape, float(y.std()))
+
+
 def gen_vctk():
     cfg = syn.VCTK_CONFIG
     sd = syn.synthetic_generator_state_dict(cfg, seed=0)
@@ -143,6 +166,7 @@ if __name__ == "__main__":
     assert _refimport.available(), "reference tree not found"
     gen_tiny()
     gen_vctk()
+    gen_f0feats()
     gen_predictors()
     gen_carryover()
     gen_morph()

@@ -162,3 +162,20 @@ def test_select_items_follows_reference_shuffle_and_n():
     assert a == b and len(set(a)) == 5 and all(0 <= k < 108 for k in a)
     assert vc_targets_for_item(8, 108) != a
     assert len(vc_targets_for_item(0, 3)) == 3
+
+
+def test_f0_median_and_f0_feats_items():
+    """sr/dataset.py:297-315: f0_median fills the unvoiced frames with the voiced median before normalising;
+    f0_feats adds the source speaker's [mean, std] as the `f0_stats` feature."""
+    from dissc_b200.inference import normalize_f0, prepare_items
+    from dissc_b200 import AttrDict
+    f0 = np.array([0.0, 100.0, 0.0, 140.0, 120.0], dtype=np.float32)
+    got = normalize_f0(f0, 110.0, 20.0, f0_median=True)
+    want = (np.array([120.0, 100.0, 120.0, 140.0, 120.0]) - 110.0) / 20.0
+    assert np.allclose(got, want)
+    assert np.allclose(normalize_f0(f0, 110.0, 20.0), [0, -0.5, 0, 1.5, 0.5])
+    h = AttrDict(f0=True, f0_normalize=True, f0_median=True, f0_feats=True, multispkr="_")
+    stats = {"p225": {"mean": 110.0, "std": 20.0}, "f0_mean": 150.0, "f0_std": 30.0}
+    items = prepare_items(h, ["/x/p225_001.wav", "/x/p999_001.wav"], [[1, 2, 3, 4, 5]] * 2, [f0, f0], ["p225", "p999"], stats)
+    assert np.allclose(items[0]["f0"], want) and np.allclose(items[0]["f0_stats"], [110.0, 20.0])
+    assert np.allclose(items[1]["f0_stats"], [150.0, 30.0])     # unknown speaker: the global statistics

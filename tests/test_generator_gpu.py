@@ -30,6 +30,47 @@ def test_golden_tiny(cuda_device):
     assert err < TOL, err
 
 
+def test_golden_f0_feats_extra_channels(cuda_device):
+    """`f0_feats` configs (sr/dataset.py:314-315, sr/inference.py:237-245, sr/models.py:216-221): `f0_stats` (B, 2) in Hz is
+    appended as two channels after the speaker embedding.  Against the reference's own output; also through
+    generate_int16, and the calls that cannot carry the feature must refuse."""
+    from dissc_b200 import _lib
+    g = load_golden("gen_f0feats.npz")
+    cfg = dict(tiny_config(), model_in_dim=tiny_config()["model_in_dim"] + 2, f0_feats=True)
+    gen = make_generator(cfg, tiny_state_dict(g), cuda_device)
+    code, f0, spkr = (torch.from_numpy(g[k]).to(cuda_device) for k in ("code", "f0", "spkr"))
+    stats = torch.from_numpy(g["f0_stats"]).to(cuda_device)
+    y = gen(code=code, f0=f0, spkr=spkr, f0_stats=stats)
+    err = np.abs(y.cpu().numpy() - g["y"]).max()
+    assert err < TOL, err
+    y2 = gen(code=code, f0=f0, spkr=spkr, f0_stats=stats.unsqueeze(-1))      # (B, 2, 1) is the same feature
+    assert torch.equal(y, y2)
+    i16 = gen.generate_int16(code, f0, spkr, f0_stats=stats).cpu().numpy()
+    assert np.array_equal(i16, (y.cpu().squeeze(1) * 32768.0).numpy().astype(np.int64).astype(np.int16))
+    with pytest.raises(ValueError):                                            # the two channels are not optional
+        gen(code=code, f0=f0, spkr=spkr)
+    with pytest.raises(_lib.DisscError, match="extra conditioning"):
+        gen.forward_host(code.cpu().pin_memory(), f0.reshape(3, -1).cpu().pin_memory(), spkr.reshape(3).cpu().pin_memory())
+    # a different speaker's statistics change the waveform
+    y3 = gen(code=code, f0=f0, spkr=spkr, f0_stats=stats + 25.0)
+    assert (y3 - y).abs().max().item() > 1e-3
+    # the shipped geometry + f0_feats runs the tensor-core path (embedding planes): against the oracle
+    from oracle import generator_oracle as go
+    cfg2 = dict(syn.VCTK_CONFIG, model_in_dim=259, f0_feats=True)
+    sd2 = syn.synthetic_generator_state_dict(cfg2, seed=5)
+    sd2["conv_pre.weight_v"][:, -2:, :] *= 0.004
+    gen2 = make_generator(cfg2, sd2, cuda_device)
+    c2, f2, s2 = syn.synthetic_inputs(2, 40, seed=31)
+    st2 = torch.tensor([[182.0, 31.0], [121.5, 18.25]])
+    ref = go.code_generator_forward(sd2, cfg2, c2, f2, s2, f0_stats=st2)
+    got = gen2(code=c2.to(cuda_device), f0=f2.to(cuda_device), spkr=s2.to(cuda_device), f0_stats=st2.to(cuda_device),
+               lengths=torch.tensor([40, 33]))
+    ref1 = go.code_generator_forward(sd2, cfg2, c2[1:, :33], f2[1:, :, :33], s2[1:], f0_stats=st2[1:])
+    assert (got[0].cpu() - ref[0]).abs().max().item() < TOL
+    assert (got[1, :, :320 * 33].cpu() - ref1[0]).abs().max().item() < TOL
+    assert gen2.set_tensor_cores(True) == 5
+
+
 def test_golden_vctk_T50(cuda_device, vctk_gen):
     """BASELINE config 1 against the reference's own output."""
     gen, sd = vctk_gen
@@ -235,9 +276,12 @@ def test_rejects_what_it_does_not_implement(cuda_device, vctk_gen):
     from dissc_b200 import AttrDict, CodeGenerator, _lib
     gen, _ = vctk_gen
     code, f0, spkr = syn.synthetic_inputs(1, 5)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):      # model_in_dim 257 leaves no room for extra conditioning channels
         gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device),
             f0_stats=torch.zeros(1, 2, device=cuda_device))
+    with pytest.raises(NotImplementedError):   # time-varying extra features are not supported
+        gen(code=code.to(cuda_device), f0=f0.to(cuda_device), spkr=spkr.to(cuda_device),
+            mel=torch.zeros(1, 2, 5, device=cuda_device))
     with pytest.raises(_lib.DisscError):
         gen(code=code, f0=f0, spkr=spkr)  # CPU tensors: no CPU path
     with pytest.raises(NotImplementedError):

@@ -19,6 +19,16 @@ def test_oracle_matches_reference_tiny():
     assert np.abs(y.numpy() - g["y"]).max() < 5e-6
 
 
+def test_oracle_matches_reference_f0_feats():
+    """`f0_feats` config: the extra `f0_stats` keyword becomes two more input channels (sr/models.py:216-221)."""
+    g = load_golden("gen_f0feats.npz")
+    cfg = dict(tiny_config(), model_in_dim=tiny_config()["model_in_dim"] + 2, f0_feats=True)
+    y = go.code_generator_forward(tiny_state_dict(g), cfg, torch.from_numpy(g["code"]), torch.from_numpy(g["f0"]),
+                                  torch.from_numpy(g["spkr"]), f0_stats=torch.from_numpy(g["f0_stats"]))
+    assert y.shape == g["y"].shape
+    assert np.abs(y.numpy() - g["y"]).max() < 5e-6
+
+
 def test_c_oracle_matches_reference_tiny():
     g = load_golden("gen_tiny.npz")
     folded = {k: v.numpy() for k, v in go.folded_state_dict(tiny_state_dict(g)).items()}
