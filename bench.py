@@ -316,6 +316,8 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         try:
             import bench_configs as bc
+            if rank == 0:   # a latency, not a throughput: one rank measures it
+                configs["configs[0]"] = bc.run_config1(gen, dev, cpu_leg=(world == 1 and not args.no_cpu_baseline))
             lm, pm = bc.build_predictors(dev)
             configs["configs[2]"] = bc.run_config3(gen, lm, pm, dev, rank, world, max_over_ranks, utts=256, iters=2)
             enc, hsd = bc.build_encoder(dev)

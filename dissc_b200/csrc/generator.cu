@@ -448,7 +448,7 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   }
   const bool epw8 = L.NC >= 128 || (L.NC == 64 && L.ctas_per_sm == 1 && g_tc_epw64 == 8 && mode != kTcGeneric);
   p.cluster2 = 0;
-  if (g_tc_cluster2 && epw8 && !L.resident && L.split_w && L.ctas_per_sm == 1 && p.n_tiles >= 2) {
+  if ((L.cluster2 < 0 ? g_tc_cluster2 : L.cluster2) && epw8 && !L.resident && L.split_w && L.ctas_per_sm == 1 && p.n_tiles >= 2) {
     const int pair_items = ((p.n_tiles + 1) / 2) * L.n_chunks;
     grid = std::min(2 * pair_items, num_sms()) & ~1;
     p.cluster2 = grid >= 2 ? 1 : 0;

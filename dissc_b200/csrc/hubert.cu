@@ -1067,6 +1067,11 @@ int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const
     if ((rc = hub_vec(g, wm, p + "final_layer_norm.bias", D, &Ly.ln2_b))) return fail(rc);
   }
   if ((rc = hub_vec(g, wm, "kmeans.cluster_centers", c.n_clusters * D, &g->cent))) return fail(rc);
+  // the encoder's streamed-weight GEMMs stream 57 B/clk/SM of weights (the stride-2 frame form also loads the taps it
+  // skips): 2-CTA clusters with one multicast weight stream are worth 1.6 % here (neutral in the vocoder, where they stay off)
+  for (int l = 0; l < 6; ++l) g->conv[l].cluster2 = 1;
+  g->proj.cluster2 = 1;
+  for (HubLayer& Ly : g->layers) Ly.qkv.cluster2 = Ly.out.cluster2 = Ly.fc1.cluster2 = Ly.fc2.cluster2 = 1;
   *out = g;
   return DISSC_OK;
 }

@@ -19,6 +19,7 @@ struct TcLayer {
   int cin8_total = 0;                // 8-channel groups per batch row of the INPUT tensor (0: Cin_pad/8)
   int groups = 0, group_c8 = 0;      // grouped conv: n_chunks groups of group_c8*8 output channels (NC-padded)
   int split_w = 1;                   // separate weight-producer thread (N >= 128 kernels)
+  int cluster2 = -1;                 // 2-CTA clusters with a multicast weight stream: 1 / 0, -1 = the global default
   int cb_split = 0, k_hi = 0;        // channel blocks >= cb_split use only their first k_hi taps (rest: structural zeros)
   size_t smem = 0;
   __half* w = nullptr;  // packed [chunk][cb][tap][KB/8][hi|lo][NC][8], device

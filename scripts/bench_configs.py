@@ -104,6 +104,48 @@ def vocode_sorted(gen, out_seq, f0, spk, out_len, vocode_batch=64):
     return n, y
 
 
+def run_config1(gen, dev, cpu_leg=False, n=30):
+    """BASELINE configs[0]: ONE utterance of 50 units (16 000 samples), Generator forward only -- the reference's own use
+    case (batch size 1, sr/inference.py:178,247): latency of an eager forward and of a CUDA-graph replay."""
+    from dissc_b200 import synthetic as syn
+    code, f0, spkr = (t.to(dev) for t in syn.synthetic_inputs(1, 50, seed=1234))
+    for _ in range(5):
+        y = gen(code=code, f0=f0, spkr=spkr)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        y = gen(code=code, f0=f0, spkr=spkr)
+    torch.cuda.synchronize(dev)
+    eager_ms = (time.perf_counter() - t0) / n * 1e3
+    gf = gen.capture_graph(1, 50, dev)
+    yg = gf(code=code, f0=f0, spkr=spkr)
+    torch.cuda.synchronize(dev)
+    same = bool(torch.equal(yg.view(-1), y.view(-1)))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        gf()
+    torch.cuda.synchronize(dev)
+    graph_ms = (time.perf_counter() - t0) / n * 1e3
+    rec = {"workload": "sr/inference.py unit of work: 1 synthetic utterance, 50 units -> 16 000 samples, Generator forward only "
+                       "(BASELINE configs[0])",
+           "latency_ms_cuda_graph": graph_ms, "latency_ms_eager": eager_ms, "graph_bit_identical_to_eager": same,
+           "samples_per_s": 16000 / graph_ms * 1e3, "launches": gen.launches_per_forward()}
+    if cpu_leg:
+        from oracle import generator_oracle as go
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+        sd = go.folded_state_dict(syn.synthetic_generator_state_dict(syn.VCTK_CONFIG, seed=0))
+        c, f, s_ = code.cpu(), f0.cpu(), spkr.cpu()
+        go.code_generator_forward(sd, syn.VCTK_CONFIG, c, f, s_)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            go.code_generator_forward(sd, syn.VCTK_CONFIG, c, f, s_)
+        cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+        rec["cpu_baseline"] = {"value": 16000 / cpu_ms * 1e3, "unit": "samples/s", "latency_ms": cpu_ms,
+                               "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "5 forwards of the oracle port on the same utterance (ATen/oneDNN, all host threads)"}
+    return rec
+
+
 def run_config3(gen, lm, pm, dev, rank, world, mx, utts=256, iters=3, vocode_batch=64):
     from dissc_b200.infer import convert_batch
     g = torch.Generator().manual_seed(1234 + rank)
