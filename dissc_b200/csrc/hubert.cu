@@ -46,6 +46,19 @@ __global__ void hub_lengths_kernel(const int* n_samples, int N, int B, int* lens
   }
 }
 
+// row_off[b] = sum of the frame counts of clips 0 .. b-1 (row_off[B] = total): where clip b starts in the packed row
+// space of the transformer stack.  B <= a few thousand: one thread.
+__global__ void hub_row_offsets_kernel(const int* lens, int B, int T, int* row_off) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      row_off[b] = acc;
+      acc += min(T, max(lens[b], 0));
+    }
+    row_off[B] = acc;
+  }
+}
+
 // ---- conv0 + GroupNorm statistics ----------------------------------------------------------------------------
 // partial[(b*nchunk + chunk)*C + c] = (sum, sumsq) of conv0 output channel c over the chunk's valid frames
 __global__ void __launch_bounds__(256) hub_conv0_stats_kernel(const float* wave, const float* w0, const int* lens0, int N,
@@ -146,10 +159,14 @@ __global__ void __launch_bounds__(256) hub_conv0_apply_kernel(const float* wave,
 // One CTA = 32 consecutive frames of one utterance x all channels: warp w owns the 8-channel groups w, w + 16, ...
 // and lane = frame, so every global access of a warp is 32 x 32 contiguous bytes; per-frame sums go through shared
 // memory (16 partials per frame).  G = C8 / 16 groups per thread (4 for 512 channels, 6 for 768).
+// `row_off` != null: the output goes to the PACKED layout of the transformer stack -- one row space for the whole batch,
+// clip b's valid frames at rows [row_off[b], row_off[b] + len_b) of a single slab set [1][C8][oTr | oTp][8] -- and only
+// valid frames are stored.
 template <int G>
 __global__ void __launch_bounds__(512) hub_layernorm_kernel(const float* in, const float* gamma, const float* beta,
-                                                            const int* lengths, int B, int C8, int T, int Tr, int Tp,
-                                                            int halo, float* out_f, __half* out_hi, __half* out_lo) {
+                                                            const int* lengths, int B, int C8, int T, int Tr, int oTr,
+                                                            int oTp, int halo, const int* row_off, float* out_f,
+                                                            __half* out_hi, __half* out_lo) {
   __shared__ float s_sum[16][32], s_sq[16][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = (T + 31) / 32;
@@ -194,7 +211,9 @@ __global__ void __launch_bounds__(512) hub_layernorm_kernel(const float* in, con
 #pragma unroll
   for (int w = 0; w < 16; ++w) q += s_sq[w][lane];
   const float rstd = rsqrtf(q / (float)(C8 * 8) + 1e-5f);
-  if (!live) return;
+  if (!live || (row_off && !valid)) return;
+  const size_t ob = row_off ? 0 : (size_t)b;                  // output batch slab / row
+  const int orow = row_off ? row_off[b] + t : t;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const int c8 = warp + g * 16;
@@ -205,9 +224,9 @@ __global__ void __launch_bounds__(512) hub_layernorm_kernel(const float* in, con
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = valid ? fmaf((x[g][e] - mean) * rstd, gm[e], bt[e]) : 0.f;
-    if (out_f) stg8(out_f + (((size_t)b * C8 + c8) * Tr + t) * 8, y);
+    if (out_f) stg8(out_f + ((ob * C8 + c8) * oTr + orow) * 8, y);
     if (out_hi) {
-      const size_t off = (((size_t)b * C8 + c8) * Tp + halo + t) * 8;
+      const size_t off = ((ob * C8 + c8) * oTp + halo + orow) * 8;
       split_store8(out_hi + off, out_lo + off, y);
     }
   }
@@ -224,8 +243,10 @@ __global__ void __launch_bounds__(512) hub_layernorm_kernel(const float* in, con
 constexpr int kAttnKT = 32;
 constexpr int kAttnKC = 8;
 constexpr int kAttnQ = 64;   // query rows (= threads) per CTA: 299 frames waste 6 % of the last tile instead of 22 % at 128
-__global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* qkv, const int* lengths, int D8, int T, int Tr,
-                                                            int Tp, int halo, __half* out_hi, __half* out_lo) {
+// Packed layout: qkv f32b [1][3*D8][Tr][8] and the output planes [1][D8][Tp][8] hold clip b's frames at rows row_off[b] + t.
+__global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* qkv, const int* lengths, const int* row_off,
+                                                            int D8, int T, int Tr, int Tp, int halo, __half* out_hi,
+                                                            __half* out_lo) {
   __shared__ __align__(16) float sK[2][kAttnKT][64];   // double-buffered: tile i+1 lands (cp.async) while tile i is used
   __shared__ __align__(16) float sV[2][kAttnKT][64];
   const int b = blockIdx.z, h = blockIdx.y;
@@ -233,7 +254,8 @@ __global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* q
   const int hf = lane & 1;                                   // which float4 of every 8-channel group
   const int tq[2] = {(int)blockIdx.x * kAttnQ + warp * 32 + (lane >> 1), (int)blockIdx.x * kAttnQ + warp * 32 + 16 + (lane >> 1)};
   const int Tv = lengths ? min(T, lengths[b]) : T;
-  const size_t bq = (size_t)b * 3 * D8;
+  const size_t bq = 0;
+  const int r0 = row_off[b];
   // stage one K / V tile: 32 keys x 64 dims each; element (key, c, e) <- f32b[(D8 + h*8 + c)][k0+key][e].  Consecutive
   // threads take consecutive float4 of a key row (conflict-free shared stores); keys past the valid length are zero-filled.
   auto stage = [&](int buf, int k0) {
@@ -242,8 +264,8 @@ __global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* q
       const int c = c4 >> 1, half = c4 & 1;
       const bool ok = k0 + key < Tv;
       const int kk = ok ? k0 + key : 0;
-      const float* gk = qkv + ((bq + D8 + h * 8 + c) * Tr + kk) * 8 + half * 4;
-      const float* gv = qkv + ((bq + 2 * D8 + h * 8 + c) * Tr + kk) * 8 + half * 4;
+      const float* gk = qkv + ((bq + D8 + h * 8 + c) * Tr + r0 + kk) * 8 + half * 4;
+      const float* gv = qkv + ((bq + 2 * D8 + h * 8 + c) * Tr + r0 + kk) * 8 + half * 4;
       const uint32_t n = ok ? 16u : 0u;     // src-size 0: the 16 destination bytes are written as zeros
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(&sK[buf][key][c4 * 4])), "l"(gk), "r"(n) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(&sV[buf][key][c4 * 4])), "l"(gv), "r"(n) : "memory");
@@ -257,7 +279,7 @@ __global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* q
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float4 a = make_float4(0, 0, 0, 0);
-      if (tq[r] < Tv) a = *reinterpret_cast<const float4*>(qkv + ((bq + h * 8 + c) * Tr + tq[r]) * 8 + hf * 4);
+      if (tq[r] < Tv) a = *reinterpret_cast<const float4*>(qkv + ((bq + h * 8 + c) * Tr + r0 + tq[r]) * 8 + hf * 4);
       q[r][c * 4 + 0] = a.x; q[r][c * 4 + 1] = a.y; q[r][c * 4 + 2] = a.z; q[r][c * 4 + 3] = a.w;
     }
 #pragma unroll
@@ -323,8 +345,8 @@ __global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* q
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int t = tq[r];
-    if (t >= T) continue;
-    const float inv = (t < Tv && l[r] > 0.f) ? 1.f / l[r] : 0.f;
+    if (t >= Tv) continue;     // packed rows: frames past the clip's length belong to the next clip
+    const float inv = l[r] > 0.f ? 1.f / l[r] : 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       // this lane's four channels of the 8-channel group: one 8-byte store per plane
@@ -336,7 +358,7 @@ __global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* q
         const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
         ll[i] = pack_half2_sat(y0 - back.x, y1 - back.y);
       }
-      const size_t off = (((size_t)b * D8 + h * 8 + c) * Tp + halo + t) * 8 + hf * 4;
+      const size_t off = (((size_t)h * 8 + c) * Tp + halo + r0 + t) * 8 + hf * 4;
       *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(hh[0], hh[1]);
       *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(ll[0], ll[1]);
     }
@@ -376,8 +398,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
 }
 
 __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(const __half* q_hi, const __half* q_lo,
-                                                                            const int* lengths, int D8, int T, int Tp_in,
-                                                                            int Tp, int halo, __half* out_hi, __half* out_lo) {
+                                                                            const int* lengths, const int* row_off, int D8,
+                                                                            int T, int Tp_in, int Tp, int halo,
+                                                                            __half* out_hi, __half* out_lo) {
   constexpr int NK = kAttnTcKeys, NKB = NK / 2;          // keys, keys per P block
   constexpr uint32_t kQPlane = 8 * 128 * 16;             // one plane of the Q tile: [c8][128 rows][16 B]
   constexpr uint32_t kKPlane = 8 * NK * 16;              // K tile: [c8][320 rows][16 B]
@@ -410,7 +433,10 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
   const size_t slab = (size_t)Tp_in * 8;                                   // halves per (b, c8) slab of the QKV planes
-  const size_t base_q = ((size_t)b * 3 * D8 + h * 8) * slab + (size_t)halo * 8;
+  // packed layout: one slab set for the batch, clip b's frames at rows row_off[b] + t (a tile may read on into the next
+  // clip's rows or the slack behind the last one: those keys are masked, those query rows are not stored)
+  const int r0 = row_off[b];
+  const size_t base_q = ((size_t)h * 8) * slab + (size_t)(halo + r0) * 8;
   const size_t base_k = base_q + (size_t)D8 * slab, base_v = base_q + (size_t)2 * D8 * slab;
   constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)((NK / 2) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = 160
   constexpr uint32_t idesc_o2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);       // N = 128
@@ -542,19 +568,19 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
   // ---- O / l -> planes (this thread's 32 of the row's 64 dims)
   {
     const int t = q0 + row;
-    const float inv = (t < Tv && l > 0.f) ? 1.f / l : 0.f;
+    const float inv = l > 0.f ? 1.f / l : 0.f;
     const uint32_t o_addr = lane_addr + NK + hsel * 32;
     float om[32], oc[32];
     tmem_ld32(o_addr, om);
     tmem_ld32(o_addr + 64, oc);
     tmem_ld_wait();
-    if (t < T) {
+    if (t < Tv) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float y[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = (om[c * 8 + e] + oc[c * 8 + e]) * inv;
-        const size_t off = (((size_t)b * D8 + h * 8 + hsel * 4 + c) * Tp + halo + t) * 8;
+        const size_t off = (((size_t)h * 8 + hsel * 4 + c) * Tp + halo + r0 + t) * 8;
         split_store8(out_hi + off, out_lo + off, y);
       }
     }
@@ -573,9 +599,10 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
 // The per-frame arithmetic and its order are unchanged -- 8 channels per lane and group, groups in order, xor-shuffle
 // tree, strict '<' so the first index wins ties -- so the units are bit-identical to the previous kernel's.
 constexpr int kKmFrames = 4;
-__global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, const float* cent, const int* lengths, int B,
-                                                              int D8, int T, int Tr, int K, long long* units,
-                                                              float* feat_out /* (B,T,D) or null */) {
+// x: packed f32b [1][D8][Tr][8], clip b's frame t at row row_off[b] + t
+__global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, const float* cent, const int* lengths,
+                                                              const int* row_off, int B, int D8, int T, int Tr, int K,
+                                                              long long* units, float* feat_out /* (B,T,D) or null */) {
   const long long w0 = ((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * kKmFrames;
   const int lane = threadIdx.x & 31;
   const long long total = (long long)B * T;
@@ -599,7 +626,7 @@ __global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, co
         const int c8 = lane + g * 32;
         float4 a = make_float4(0, 0, 0, 0), c = a;
         if (valid[f] && c8 < D8) {
-          const float* p = x + (((size_t)b * D8 + c8) * Tr + t) * 8;
+          const float* p = x + ((size_t)c8 * Tr + row_off[b] + t) * 8;
           a = *reinterpret_cast<const float4*>(p);
           c = *reinterpret_cast<const float4*>(p + 4);
           if (feat_out) {
@@ -670,14 +697,15 @@ __global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, co
 // broadcast LDS.128).  Distances are summed per chunk and then across chunks (two-level fp32 sum), the argmin runs
 // over (distance, index) pairs -- lowest index on ties -- first inside the thread, then across the 16 centroid lanes.
 constexpr int kKmTileT = 32, kKmMaxK = 128, kKmChunk = 32;
-__global__ void __launch_bounds__(256) hub_kmeans_tiled_kernel(const float* x, const float* cent, const int* lengths, int B,
-                                                               int D8, int T, int Tr, int K, long long* units,
-                                                               float* feat_out /* (B,T,D) or null */) {
+__global__ void __launch_bounds__(256) hub_kmeans_tiled_kernel(const float* x, const float* cent, const int* lengths,
+                                                               const int* row_off, int B, int D8, int T, int Tr, int K,
+                                                               long long* units, float* feat_out /* (B,T,D) or null */) {
   __shared__ __align__(16) float sx[4 * kKmTileT * 8];            // [c8 of the chunk][t][8]
   __shared__ __align__(16) float sc[8 * kKmMaxK * 4];             // [channel quad of the chunk][j][4]
   const int tiles_per_b = (T + kKmTileT - 1) / kKmTileT;
   const int b = blockIdx.x / tiles_per_b, t0 = (blockIdx.x - b * tiles_per_b) * kKmTileT;
   const int Tv = lengths ? min(T, lengths[b]) : T;
+  const int r0 = row_off[b];                                      // packed input: clip b's frame t at row r0 + t
   const int tid = threadIdx.x, cg = tid & 15, fg = tid >> 4;      // centroid lane, frame pair
   const int D = D8 * 8;
   float tot[2][8];
@@ -692,7 +720,7 @@ __global__ void __launch_bounds__(256) hub_kmeans_tiled_kernel(const float* x, c
       const int c8 = tid >> 6, r = (tid >> 1) & 31, half = tid & 1;
       const int t = t0 + r;
       float4 v = make_float4(0, 0, 0, 0);
-      if (t < Tv) v = *reinterpret_cast<const float4*>(x + (((size_t)b * D8 + d0 / 8 + c8) * Tr + t) * 8 + half * 4);
+      if (t < Tv) v = *reinterpret_cast<const float4*>(x + ((size_t)(d0 / 8 + c8) * Tr + r0 + t) * 8 + half * 4);
       *reinterpret_cast<float4*>(&sx[(c8 * kKmTileT + r) * 8 + half * 4]) = v;
       if (feat_out && t < T) *reinterpret_cast<float4*>(feat_out + ((size_t)b * T + t) * D + d0 + c8 * 8 + half * 4) = v;
       // centroid chunk: K rows x 32 channels -> [quad][j][4]
@@ -881,8 +909,25 @@ static HubShapes hub_shapes(int N) {
 }
 static size_t ru(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Packed row space of the transformer stack: after pos_conv no op looks across frames except attention, which is per
+// clip anyway, so the B clips' VALID frames are laid end to end in one [1][C/8][rows][8] slab set and every GEMM sees
+// M = sum of the frame counts instead of B x roundup(T, 128): 75 row tiles instead of 96 for 32 clips of 299 frames.
+// R: upper bound of the used rows; Rr: rows of the f32b slabs; Rp: rows of the plane slabs -- halo, then Rr, then slack
+// for the attention tiles that start at a clip's first row and run 320 keys / 384 query rows on whatever follows.
+struct HubPacked {
+  int R, Rr, Rp;
+};
+static HubPacked hub_packed_rows(int B, int T) {
+  HubPacked k;
+  k.R = B * T;
+  k.Rr = (int)ru(k.R, 128);
+  k.Rp = k.Rr + 2 * kHubHalo + 384;
+  return k;
+}
+
 struct HubBuffers {
   int* lens;
+  int* row_off;   // B + 1: first packed row of every clip, then the total
   float2* gn_partial;
   float2* gn_ss;
   __half* dA[2];  // de-interleaved plane pairs (hi at [0], lo at hi + plane_elems)
@@ -900,6 +945,7 @@ static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
   const int C = c.conv_dim, D = c.embed_dim;
   const int nchunk = (std::max(s.T[0], 1) + kConv0Chunk - 1) / kConv0Chunk;
   b.lens = (int*)bp.take((size_t)7 * B * sizeof(int));
+  b.row_off = (int*)bp.take((size_t)(B + 1) * sizeof(int));
   b.gn_partial = (float2*)bp.take((size_t)B * nchunk * C * sizeof(float2));
   b.gn_ss = (float2*)bp.take((size_t)B * C * sizeof(float2));
   auto plane_bytes = [&](int ch, int rows) { return (size_t)B * (ch / 8) * (ru(std::max(rows, 1), 128) + 2 * kHubHalo) * 16 + 4096; };
@@ -910,6 +956,9 @@ static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
   const int T = std::max(s.T[6], 1);
   const size_t Tr = ru(T, 128);
   auto f32b_bytes = [&](int ch) { return (size_t)B * (ch / 8) * Tr * 32 + 4096; };
+  // the transformer stack runs on ONE packed row space (hub_packed_rows): its plane buffers hold whichever is larger
+  const HubPacked pk = hub_packed_rows(B, T);
+  auto tplane_bytes = [&](int ch) { return std::max(plane_bytes(ch, T), (size_t)(ch / 8) * pk.Rp * 16 + 4096); };
   b.X6 = (float*)bp.take(f32b_bytes(C));
   b.X7 = (float*)bp.take(f32b_bytes(D));
   b.X8 = (float*)bp.take(f32b_bytes(D));
@@ -919,19 +968,22 @@ static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
   for (int i = 0; i < 2; ++i) {
     b.P6[i] = (__half*)bp.take(plane_bytes(C, T));
     b.P7[i] = (__half*)bp.take(plane_bytes(D, T));
-    b.PH[i] = (__half*)bp.take(plane_bytes(D, T));
-    b.PA[i] = (__half*)bp.take(plane_bytes(D, T));
-    b.PF[i] = (__half*)bp.take(plane_bytes(c.ffn_dim, T));
-    b.PQ[i] = (__half*)bp.take(plane_bytes(3 * D, T));
+    b.PH[i] = (__half*)bp.take(tplane_bytes(D));
+    b.PA[i] = (__half*)bp.take(tplane_bytes(D));
+    b.PF[i] = (__half*)bp.take(tplane_bytes(c.ffn_dim));
+    b.PQ[i] = (__half*)bp.take(tplane_bytes(3 * D));
   }
   b.total = bp.off;
   return b;
 }
 
+// row_off == null: per-clip layout in and out (oTr = Tr, oTp = Tp); else packed output (see the kernel)
 static int hub_layernorm(const float* in, const float* gw, const float* gb, const int* lengths, int B, int C, int T, int Tr,
-                         int Tp, float* out_f, __half* out_hi, __half* out_lo, cudaStream_t st) {
+                         int Tp, float* out_f, __half* out_hi, __half* out_lo, cudaStream_t st, const int* row_off = nullptr,
+                         int oTr = 0, int oTp = 0) {
   const int blocks = B * ((T + 31) / 32);
-#define HUB_LN(G) hub_layernorm_kernel<G><<<blocks, 512, 0, st>>>(in, gw, gb, lengths, B, C / 8, T, Tr, Tp, kHubHalo, out_f, out_hi, out_lo)
+  if (!row_off) { oTr = Tr; oTp = Tp; }
+#define HUB_LN(G) hub_layernorm_kernel<G><<<blocks, 512, 0, st>>>(in, gw, gb, lengths, B, C / 8, T, Tr, oTr, oTp, kHubHalo, row_off, out_f, out_hi, out_lo)
   switch (C) {
     case 256: HUB_LN(2); break;
     case 512: HUB_LN(4); break;
@@ -1176,12 +1228,27 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     p.a_hi = bf.P7[0]; p.a_lo = bf.P7[1]; p.bias = g->pos_b; p.pre_act = 2; p.res = bf.X7; p.out_f32b = bf.X8;
     HUB_TRY(launch_conv_tc(p, g->pos, T, st));
   }
+  // ---- transformer stack on the packed row space (HubPacked) ----
+  const HubPacked pk = hub_packed_rows(B, T);
+  const int* row_off = bf.row_off;
+  const int* len_all = bf.row_off + B;   // "length" of the one packed pseudo-clip
+  hub_row_offsets_kernel<<<1, 32, 0, st>>>(lenT, B, T, bf.row_off);
+  DISSC_CUDA(cudaGetLastError());
+  // PH / PA are written row by row (LayerNorm, attention: valid frames only) and read tile by tile: the rows between the
+  // total and the end of the last tile must hold finite numbers.  PF / PQ are written by GEMM epilogues, whole tiles.
   for (int i = 0; i < 2; ++i) {
-    __half** P = i == 0 ? bf.PH : bf.PA;
-    HUB_TRY(launch_zero_halos(P[0], P[1], B * D / 8, Tp, T, st, kHubHalo));
+    DISSC_CUDA(cudaMemsetAsync(bf.PH[i], 0, (size_t)(D / 8) * pk.Rp * 16, st));
+    DISSC_CUDA(cudaMemsetAsync(bf.PA[i], 0, (size_t)(D / 8) * pk.Rp * 16, st));
   }
-  HUB_TRY(launch_zero_halos(bf.PF[0], bf.PF[1], B * c.ffn_dim / 8, Tp, T, st, kHubHalo));
-  HUB_TRY(hub_layernorm(bf.X8, g->eln_w, g->eln_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
+  HUB_TRY(hub_layernorm(bf.X8, g->eln_w, g->eln_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st, row_off, pk.Rr, pk.Rp));
+  auto pbase = [&]() {
+    TcParams p{};
+    p.lengths = len_all; p.len_mul = 1; p.B = 1; p.T = pk.R; p.Tr = pk.Rr; p.Tp = pk.Rp; p.Tp_in = pk.Rp; p.halo = kHubHalo;
+    return p;
+  };
+  auto packed_ln = [&](const float* in, const float* w, const float* bsv) {
+    return hub_layernorm(in, w, bsv, len_all, 1, D, pk.R, pk.Rr, pk.Rp, bf.H, bf.PH[0], bf.PH[1], st);
+  };
   // attention on the tensor cores when all keys of a clip fit one CTA (<= 320 frames = 102 000 samples; BASELINE
   // configs[3] clips have 299); longer batches use the CUDA-core kernel.  DISSC_HUB_ATTN_TC=0 forces the latter.
   if (g_hub_attn_tc < 0) {
@@ -1193,7 +1260,7 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
   for (int l = 0; l < c.n_layers; ++l) {
     const HubLayer& Ly = g->layers[l];
     {
-      TcParams p = base();
+      TcParams p = pbase();
       p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = Ly.qkv_b;
       if (attn_tc) {
         // planes for the tensor-core attention; leaky-relu with slope 1 is the identity (max(v, v * 1)) and keeps the
@@ -1202,42 +1269,42 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
       } else {
         p.out_f32b = bf.QKV;
       }
-      HUB_TRY(launch_conv_tc(p, Ly.qkv, T, st));
+      HUB_TRY(launch_conv_tc(p, Ly.qkv, pk.R, st));
     }
     if (attn_tc) {
       hub_attention_tc_kernel<<<dim3((T + 127) / 128, c.n_heads, B), kAttnTcThreads, kAttnTcSmem, st>>>(
-          bf.PQ[0], bf.PQ[1], lenT, D / 8, T, Tp, Tp, kHubHalo, bf.PA[0], bf.PA[1]);
+          bf.PQ[0], bf.PQ[1], lenT, row_off, D / 8, T, pk.Rp, pk.Rp, kHubHalo, bf.PA[0], bf.PA[1]);
     } else {
-      hub_attention_kernel<<<dim3((T + kAttnQ - 1) / kAttnQ, c.n_heads, B), kAttnQ, 0, st>>>(bf.QKV, lenT, D / 8, T, Tr, Tp,
-                                                                                           kHubHalo, bf.PA[0], bf.PA[1]);
+      hub_attention_kernel<<<dim3((T + kAttnQ - 1) / kAttnQ, c.n_heads, B), kAttnQ, 0, st>>>(
+          bf.QKV, lenT, row_off, D / 8, T, pk.Rr, pk.Rp, kHubHalo, bf.PA[0], bf.PA[1]);
     }
     DISSC_CUDA(cudaGetLastError());
     {
-      TcParams p = base();
+      TcParams p = pbase();
       p.a_hi = bf.PA[0]; p.a_lo = bf.PA[1]; p.bias = Ly.out_b; p.res = bf.H; p.out_f32b = bf.Y;
-      HUB_TRY(launch_conv_tc(p, Ly.out, T, st));
+      HUB_TRY(launch_conv_tc(p, Ly.out, pk.R, st));
     }
-    HUB_TRY(hub_layernorm(bf.Y, Ly.ln1_w, Ly.ln1_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
+    HUB_TRY(packed_ln(bf.Y, Ly.ln1_w, Ly.ln1_b));
     {
-      TcParams p = base();
+      TcParams p = pbase();
       p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = Ly.fc1_b; p.out_hi = bf.PF[0]; p.out_lo = bf.PF[1]; p.plane_act = 2;
-      HUB_TRY(launch_conv_tc(p, Ly.fc1, T, st));
+      HUB_TRY(launch_conv_tc(p, Ly.fc1, pk.R, st));
     }
     {
-      TcParams p = base();
+      TcParams p = pbase();
       p.a_hi = bf.PF[0]; p.a_lo = bf.PF[1]; p.bias = Ly.fc2_b; p.res = bf.H; p.out_f32b = bf.Y;
-      HUB_TRY(launch_conv_tc(p, Ly.fc2, T, st));
+      HUB_TRY(launch_conv_tc(p, Ly.fc2, pk.R, st));
     }
-    HUB_TRY(hub_layernorm(bf.Y, Ly.ln2_w, Ly.ln2_b, lenT, B, D, T, Tr, Tp, bf.H, bf.PH[0], bf.PH[1], st));
+    HUB_TRY(packed_ln(bf.Y, Ly.ln2_w, Ly.ln2_b));
   }
   {
     if (c.n_clusters <= kKmMaxK && D % kKmChunk == 0) {
       hub_kmeans_tiled_kernel<<<B * ((T + kKmTileT - 1) / kKmTileT), 256, 0, st>>>(
-          bf.H, g->cent, lenT, B, D / 8, T, Tr, c.n_clusters, reinterpret_cast<long long*>(units), features);
+          bf.H, g->cent, lenT, row_off, B, D / 8, T, pk.Rr, c.n_clusters, reinterpret_cast<long long*>(units), features);
     } else {
       const long long threads = (((long long)B * T + kKmFrames - 1) / kKmFrames) * 32;
-      hub_kmeans_f32b_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(bf.H, g->cent, lenT, B, D / 8, T, Tr, c.n_clusters,
-                                                                           reinterpret_cast<long long*>(units), features);
+      hub_kmeans_f32b_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(
+          bf.H, g->cent, lenT, row_off, B, D / 8, T, pk.Rr, c.n_clusters, reinterpret_cast<long long*>(units), features);
     }
     DISSC_CUDA(cudaGetLastError());
   }
