@@ -60,9 +60,26 @@ __global__ void hub_row_offsets_kernel(const int* lens, int B, int T, int* row_o
 }
 
 // ---- conv0 + GroupNorm statistics ----------------------------------------------------------------------------
-// partial[(b*nchunk + chunk)*C + c] = (sum, sumsq) of conv0 output channel c over the chunk's valid frames
-__global__ void __launch_bounds__(256) hub_conv0_stats_kernel(const float* wave, const float* w0, const int* lens0, int N,
-                                                              int C, int nchunk, float2* partial) {
+// GroupNorm(C groups, C channels) needs, per clip and channel, the mean and variance over time of y_c[t] = sum_k w_c[k]
+// x[5t + k].  Both are functions of 65 MOMENTS OF THE WAVE that do not depend on the channel:
+//     S[k]    = sum_t x[5t + k]                    (10)         mean_c   = w_c . S / n
+//     R[k][j] = sum_t x[5t + k] x[5t + j], k <= j  (55)         E[y_c^2] = w_c^T R w_c / n
+// so the statistics cost 65 multiply-adds per frame instead of a full 512-channel conv0 pass (0.19 ms -> 0.02 ms at
+// 32 x 96 000 samples).  A filter that rejects most of the signal makes w^T R w a sum of large cancelling terms, so the
+// moments are accumulated in fp64 (products of two fp32 numbers are exact there) and so is the quadratic form.
+constexpr int kWaveMoments = 65;
+// moment m -> (k, j): m < 10: S[m] (k = m, j = -1); else the pairs k <= j in row-major order
+__device__ __forceinline__ void wave_moment_kj(int m, int& k, int& j) {
+  if (m < kConv0K) { k = m; j = -1; return; }
+  int r = m - kConv0K;
+  k = 0;
+  while (r >= kConv0K - k) { r -= kConv0K - k; ++k; }
+  j = k + r;
+}
+
+// partial[(b*nchunk + chunk)*65 + m]: moment m over the chunk's valid frames.  Four threads per moment (frames mod 4).
+__global__ void __launch_bounds__(256) hub_wave_moments_kernel(const float* wave, const int* lens0, int N, int nchunk,
+                                                               double* partial) {
   __shared__ float sw[kConv0Chunk * kConv0S + kConv0K];
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int T0 = lens0[b];
@@ -71,40 +88,67 @@ __global__ void __launch_bounds__(256) hub_conv0_stats_kernel(const float* wave,
   const int ns = nf > 0 ? (nf - 1) * kConv0S + kConv0K : 0;
   for (int i = threadIdx.x; i < ns; i += blockDim.x) sw[i] = wave[(size_t)b * N + (size_t)t0 * kConv0S + i];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float w[kConv0K];
-#pragma unroll
-    for (int j = 0; j < kConv0K; ++j) w[j] = w0[c * kConv0K + j];
-    float s = 0.f, q = 0.f;
-    for (int f = 0; f < nf; ++f) {
-      float v = 0.f;
-#pragma unroll
-      for (int j = 0; j < kConv0K; ++j) v = fmaf(sw[f * kConv0S + j], w[j], v);
-      s += v;
-      q = fmaf(v, v, q);
+  const int sub = threadIdx.x & 3;
+  for (int m = threadIdx.x >> 2; m < 128; m += 64) {   // every thread runs both rounds: the shuffles need whole warps
+    int k = 0, j = -1;
+    if (m < kWaveMoments) wave_moment_kj(m, k, j);
+    double acc = 0.0;
+    if (m < kWaveMoments) {
+      for (int f = sub; f < nf; f += 4) {
+        const double xk = (double)sw[f * kConv0S + k];
+        acc = j < 0 ? acc + xk : fma(xk, (double)sw[f * kConv0S + j], acc);
+      }
     }
-    partial[((size_t)b * nchunk + chunk) * C + c] = make_float2(s, q);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (sub == 0 && m < kWaveMoments) partial[((size_t)b * nchunk + chunk) * kWaveMoments + m] = acc;
   }
 }
 
-// scale/shift of GroupNorm(C groups, C channels): y = (x - mean) * rstd * gamma + beta  (biased variance, eps 1e-5)
-__global__ void hub_gn_finalize_kernel(const float2* partial, const float* gamma, const float* beta, const int* lens0,
-                                       int B, int C, int nchunk, float2* scale_shift) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * C) return;
-  const int b = i / C, c = i - b * C;
-  double s = 0.0, q = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    const float2 p = partial[((size_t)b * nchunk + k) * C + c];
-    s += p.x;
-    q += p.y;
+// scale/shift of GroupNorm(C groups, C channels): y = (x - mean) * rstd * gamma + beta  (biased variance, eps 1e-5).
+// One CTA per clip: the chunk partials are summed into shared memory, then every thread takes channels.
+__global__ void __launch_bounds__(256) hub_gn_finalize_kernel(const double* partial, const float* w0, const float* gamma,
+                                                              const float* beta, const int* lens0, int C, int nchunk,
+                                                              float2* scale_shift) {
+  __shared__ double s_mom[kWaveMoments];
+  __shared__ double s_R[kConv0K][kConv0K];
+  const int b = blockIdx.x;
+  const int sub = threadIdx.x & 3;
+  for (int m = threadIdx.x >> 2; m < 128; m += 64) {
+    double acc = 0.0;
+    if (m < kWaveMoments)
+      for (int k = sub; k < nchunk; k += 4) acc += partial[((size_t)b * nchunk + k) * kWaveMoments + m];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (sub == 0 && m < kWaveMoments) s_mom[m] = acc;
   }
+  __syncthreads();
+  if (threadIdx.x >= kConv0K && threadIdx.x < kWaveMoments) {
+    int k, j;
+    wave_moment_kj(threadIdx.x, k, j);
+    s_R[k][j] = s_R[j][k] = s_mom[threadIdx.x];
+  }
+  __syncthreads();
   const double n = (double)max(lens0[b], 1);
-  const double mean = s / n;
-  const double var = fmax(q / n - mean * mean, 0.0);
-  const double rstd = 1.0 / sqrt(var + 1e-5);
-  const float sc = (float)(rstd * gamma[c]);
-  scale_shift[i] = make_float2(sc, (float)(beta[c] - mean * rstd * gamma[c]));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double w[kConv0K];
+#pragma unroll
+    for (int k = 0; k < kConv0K; ++k) w[k] = (double)w0[c * kConv0K + k];
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int k = 0; k < kConv0K; ++k) {
+      s = fma(w[k], s_mom[k], s);
+      double row = 0.0;
+#pragma unroll
+      for (int j = 0; j < kConv0K; ++j) row = fma(w[j], s_R[k][j], row);
+      q = fma(w[k], row, q);
+    }
+    const double mean = s / n;
+    const double var = fmax(q / n - mean * mean, 0.0);
+    const double rstd = 1.0 / sqrt(var + 1e-5);
+    const float sc = (float)(rstd * gamma[c]);
+    scale_shift[(size_t)b * C + c] = make_float2(sc, (float)(beta[c] - mean * rstd * gamma[c]));
+  }
 }
 
 // conv0 recomputed, normalised, GELU'd and written as split planes, de-interleaved for the stride-2 conv1:
@@ -379,7 +423,7 @@ __global__ void __launch_bounds__(kAttnQ, 6) hub_attention_kernel(const float* q
 // fp32-accurate like every other GEMM here (the units must not move), at tensor-core instead of FMA-pipe speed.
 int g_hub_attn_tc = -1;               // dissc_tc_set_tuning key 4 / env DISSC_HUB_ATTN_TC (default 1)
 constexpr int kAttnTcKeys = 320;      // keys per CTA (multiple of 16, two N = 160 chunks for S)
-constexpr int kAttnTcThreads = 256;
+constexpr int kAttnTcThreads = 512;   // four threads per query row (TMEM lane): the kernel is latency-bound, warps are what it needs
 constexpr uint32_t kVtStride = 2048 + 16;                    // bytes between key groups of the V^T tile (bank padding)
 constexpr size_t kAttnTcSmem = 32768 + 81920 + (kAttnTcKeys / 8) * kVtStride + 64;   // Q | K (later P) | V^T | barriers
 
@@ -395,6 +439,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
       : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(const __half* q_hi, const __half* q_lo,
@@ -413,9 +468,9 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
   uint64_t* qk_full = bars;      // TMA: Q and K tiles landed
   uint64_t* mma_done = bars + 1; // tcgen05.commit after S, after each PV block
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_red[2][128];   // per-row partial max / sum of the two threads that share a row
-  // two threads per query row: thread r and thread r + 128 (warps w and w + 4 address the same TMEM lane quarter) take
-  // alternate 32-key chunks of every pass and alternate halves of the output
+  __shared__ float s_red[4][128];   // per-row partial max / sum of the four threads that share a row
+  // four threads per query row: threads r, r + 128, r + 256, r + 384 (warps w, w + 4, w + 8, w + 12 address the same TMEM
+  // lane quarter) take every fourth 16-key chunk of every pass and a quarter of the output each
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, hsel = tid >> 7;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int Tv = lengths ? min(T, lengths[b]) : T;
@@ -502,18 +557,18 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
   tc_fence_after();
   const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   float mx = -INFINITY;
-  for (int c0 = hsel * 32; c0 < NK; c0 += 64) {
+  for (int c0 = hsel * 16; c0 < NK; c0 += 64) {
     if (c0 >= Tv) break;
-    float sc[32];
-    tmem_ld32(lane_addr + c0, sc);
+    float sc[16];
+    tmem_ld16(lane_addr + c0, sc);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < 16; ++i)
       if (c0 + i < Tv) mx = fmaxf(mx, sc[i]);
   }
   s_red[hsel][row] = mx;
   __syncthreads();
-  mx = fmaxf(s_red[0][row], s_red[1][row]);
+  mx = fmaxf(fmaxf(s_red[0][row], s_red[1][row]), fmaxf(s_red[2][row], s_red[3][row]));
   constexpr float kLog2e = 1.4426950408889634f;
   const float mxl = mx * kLog2e;
   float l = 0.f;
@@ -521,15 +576,15 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
   const uint32_t pd = umma_desc_lo(smem_u32(sK), 128 * 16), vd = umma_desc_lo(smem_u32(sV), kVtStride);
   for (int blk = 0; blk < 2; ++blk) {
     // P block = keys [blk*160, blk*160 + 160): exp(s - max), fp16 hi / lo, K-major [key group][row][8 keys]
-    for (int ci = hsel; ci < NKB / 32; ci += 2) {
-      const int c0 = blk * NKB + ci * 32;
-      float sc[32];
+    for (int ci = hsel; ci < NKB / 16; ci += 4) {
+      const int c0 = blk * NKB + ci * 16;
+      float sc[16];
       if (c0 < Tv) {
-        tmem_ld32(lane_addr + c0, sc);
+        tmem_ld16(lane_addr + c0, sc);
         tmem_ld_wait();
       }
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
+      for (int g8 = 0; g8 < 2; ++g8) {
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -538,7 +593,7 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
           pv[i] = (key < Tv) ? exp2f(fmaf(sc[g8 * 8 + i], kLog2e, -mxl)) : 0.f;
           l += pv[i];
         }
-        unsigned char* dst = sK + (size_t)(ci * 4 + g8) * 2048 + row * 16;
+        unsigned char* dst = sK + (size_t)(ci * 2 + g8) * 2048 + row * 16;
         split_store8(reinterpret_cast<__half*>(dst), reinterpret_cast<__half*>(dst + kPPlane), pv);
       }
     }
@@ -564,23 +619,23 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
   }
   s_red[hsel][row] = l;
   __syncthreads();
-  l = s_red[0][row] + s_red[1][row];
-  // ---- O / l -> planes (this thread's 32 of the row's 64 dims)
+  l = (s_red[0][row] + s_red[1][row]) + (s_red[2][row] + s_red[3][row]);
+  // ---- O / l -> planes (this thread's 16 of the row's 64 dims)
   {
     const int t = q0 + row;
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    const uint32_t o_addr = lane_addr + NK + hsel * 32;
-    float om[32], oc[32];
-    tmem_ld32(o_addr, om);
-    tmem_ld32(o_addr + 64, oc);
+    const uint32_t o_addr = lane_addr + NK + hsel * 16;
+    float om[16], oc[16];
+    tmem_ld16(o_addr, om);
+    tmem_ld16(o_addr + 64, oc);
     tmem_ld_wait();
     if (t < Tv) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float y[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = (om[c * 8 + e] + oc[c * 8 + e]) * inv;
-        const size_t off = (((size_t)h * 8 + hsel * 4 + c) * Tp + halo + r0 + t) * 8;
+        const size_t off = (((size_t)h * 8 + hsel * 2 + c) * Tp + halo + r0 + t) * 8;
         split_store8(out_hi + off, out_lo + off, y);
       }
     }
@@ -928,7 +983,7 @@ static HubPacked hub_packed_rows(int B, int T) {
 struct HubBuffers {
   int* lens;
   int* row_off;   // B + 1: first packed row of every clip, then the total
-  float2* gn_partial;
+  double* gn_partial;   // [B][nchunk][65] wave moments
   float2* gn_ss;
   __half* dA[2];  // de-interleaved plane pairs (hi at [0], lo at hi + plane_elems)
   __half* dB[2];
@@ -946,7 +1001,7 @@ static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
   const int nchunk = (std::max(s.T[0], 1) + kConv0Chunk - 1) / kConv0Chunk;
   b.lens = (int*)bp.take((size_t)7 * B * sizeof(int));
   b.row_off = (int*)bp.take((size_t)(B + 1) * sizeof(int));
-  b.gn_partial = (float2*)bp.take((size_t)B * nchunk * C * sizeof(float2));
+  b.gn_partial = (double*)bp.take((size_t)B * nchunk * kWaveMoments * sizeof(double));
   b.gn_ss = (float2*)bp.take((size_t)B * C * sizeof(float2));
   auto plane_bytes = [&](int ch, int rows) { return (size_t)B * (ch / 8) * (ru(std::max(rows, 1), 128) + 2 * kHubHalo) * 16 + 4096; };
   // ping-pong: dA holds D0, D2, D4; dB holds D1, D3, D5
@@ -1164,10 +1219,9 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
   {
     const int T0 = s.T[0];
     const int nchunk = (T0 + kConv0Chunk - 1) / kConv0Chunk;
-    hub_conv0_stats_kernel<<<dim3(nchunk, B), 256, 0, st>>>(wave, g->w0, bf.lens, N, C, nchunk, bf.gn_partial);
+    hub_wave_moments_kernel<<<dim3(nchunk, B), 256, 0, st>>>(wave, bf.lens, N, nchunk, bf.gn_partial);
     DISSC_CUDA(cudaGetLastError());
-    hub_gn_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(bf.gn_partial, g->gn_w, g->gn_b, bf.lens, B, C, nchunk,
-                                                                bf.gn_ss);
+    hub_gn_finalize_kernel<<<B, 256, 0, st>>>(bf.gn_partial, g->w0, g->gn_w, g->gn_b, bf.lens, C, nchunk, bf.gn_ss);
     DISSC_CUDA(cudaGetLastError());
     const int Tq = s.Tq[0];
     const int Tp = (int)ru(Tq, 128) + 2 * kHubHalo;
