@@ -21,6 +21,7 @@
 // evaluation to ~1e-5 and the argmin changes only on near-ties (tests report the margin).
 #include <cmath>
 #include <cstring>
+#include <cfloat>
 #include <map>
 #include <string>
 #include <vector>
@@ -168,26 +169,28 @@ __global__ void __launch_bounds__(256) hub_conv0_apply_kernel(const float* wave,
   for (int i = threadIdx.x; i < C * kConv0K; i += blockDim.x) sW[i] = w0[i];
   __syncthreads();
   const int c8n = C / 8;
-  // item = (c8, phase, q): lanes run over q so a warp writes 32 consecutive rows of one slab
-  const int qn = kConv0Chunk / 2;
-  for (int item = threadIdx.x; item < c8n * 2 * qn; item += blockDim.x) {
-    const int q = item % qn;
-    const int ph = (item / qn) & 1;
-    const int c8 = item / (2 * qn);
-    const int f = 2 * q + ph;  // frame inside the chunk
-    float v[8];
-    if (f < nf) {
-      float x[kConv0K];
+  // thread = (q, phase) of the chunk -- lanes run over q, so a warp writes 32 consecutive rows of one slab -- and walks
+  // the channel groups: its frame, the ten samples under it and all address arithmetic are loop-invariant
+  constexpr int qn = kConv0Chunk / 2;
+  static_assert(256 % (2 * qn) == 0, "thread -> (q, phase) mapping");
+  const int q = threadIdx.x % qn, ph = (threadIdx.x / qn) & 1;
+  const int f = 2 * q + ph;  // frame inside the chunk
+  const bool have = f < nf;
+  float x[kConv0K];
 #pragma unroll
-      for (int j = 0; j < kConv0K; ++j) x[j] = sw[f * kConv0S + j];
+  for (int j = 0; j < kConv0K; ++j) x[j] = have ? sw[f * kConv0S + j] : 0.f;
+  const float2* ss = scale_shift + (size_t)b * C;
+  for (int c8 = threadIdx.x / (2 * qn); c8 < c8n; c8 += 256 / (2 * qn)) {
+    float v[8];
+    if (have) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = c8 * 8 + e;
         float a = 0.f;
 #pragma unroll
         for (int j = 0; j < kConv0K; ++j) a = fmaf(x[j], sW[c * kConv0K + j], a);
-        const float2 ss = scale_shift[(size_t)b * C + c];
-        v[e] = gelu_erf(fmaf(a, ss.x, ss.y));
+        const float2 sc = __ldg(ss + c);
+        v[e] = gelu_erf(fmaf(a, sc.x, sc.y));
       }
     } else {
 #pragma unroll
@@ -745,99 +748,52 @@ __global__ void __launch_bounds__(256) hub_kmeans_f32b_kernel(const float* x, co
   }
 }
 
-// Tiled form of the same assignment (round 2): a CTA takes 32 frames of one clip and ALL centroids, so every centroid
-// value is read from L2 once per CTA instead of once per warp.  256 threads = 16 frame pairs x 16 centroid lanes; a
-// thread accumulates the squared distances of its 2 frames to centroids cg, cg + 16, ..., cg + 112 over 32-channel
-// chunks staged in shared memory (x chunk [4 c8][32 t][8], centroid chunk [8 quads][128 j][4]: conflict-free /
-// broadcast LDS.128).  Distances are summed per chunk and then across chunks (two-level fp32 sum), the argmin runs
-// over (distance, index) pairs -- lowest index on ties -- first inside the thread, then across the 16 centroid lanes.
-constexpr int kKmTileT = 32, kKmMaxK = 128, kKmChunk = 32;
-__global__ void __launch_bounds__(256) hub_kmeans_tiled_kernel(const float* x, const float* cent, const int* lengths,
-                                                               const int* row_off, int B, int D8, int T, int Tr, int K,
-                                                               long long* units, float* feat_out /* (B,T,D) or null */) {
-  __shared__ __align__(16) float sx[4 * kKmTileT * 8];            // [c8 of the chunk][t][8]
-  __shared__ __align__(16) float sc[8 * kKmMaxK * 4];             // [channel quad of the chunk][j][4]
-  const int tiles_per_b = (T + kKmTileT - 1) / kKmTileT;
-  const int b = blockIdx.x / tiles_per_b, t0 = (blockIdx.x - b * tiles_per_b) * kKmTileT;
+
+// K <= 128 centroids: the assignment is a GEMM.  argmin_j |x - c_j|^2 = argmin_j (|c_j|^2 - 2 x.c_j) -- the form
+// fairseq's ApplyKmeans and sklearn's predict evaluate -- so the centroids are one more streamed-weight layer (W = -2 C,
+// bias = |c|^2 in fp64, +FLT_MAX for the padded columns) fed by the planes the layer-6 LayerNorm writes anyway: 75 row
+// tiles x 3 split-fp16 MMAs instead of 1.9 G CUDA-core multiply-adds (0.18 -> 0.02 ms per 32 clips).  This kernel then
+// takes the row minimum: dist f32b [1][16][Tr][8] (packed rows), lowest index on ties, -1 past the valid length.
+constexpr int kKmMaxK = 128;
+__global__ void __launch_bounds__(128) hub_kmeans_argmin_kernel(const float* dist, const int* lengths, const int* row_off,
+                                                                int T, int Tr, long long* units) {
+  const int tiles_per_b = (T + 127) / 128;
+  const int b = blockIdx.x / tiles_per_b, t = (blockIdx.x - b * tiles_per_b) * 128 + threadIdx.x;
+  if (t >= T) return;
   const int Tv = lengths ? min(T, lengths[b]) : T;
-  const int r0 = row_off[b];                                      // packed input: clip b's frame t at row r0 + t
-  const int tid = threadIdx.x, cg = tid & 15, fg = tid >> 4;      // centroid lane, frame pair
-  const int D = D8 * 8;
-  float tot[2][8];
-#pragma unroll
-  for (int f = 0; f < 2; ++f)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tot[f][i] = 0.f;
-  for (int d0 = 0; d0 < D; d0 += kKmChunk) {
-    __syncthreads();   // everyone is done with the previous chunk
-    {
-      // x chunk: 4 slabs x 32 rows x 32 bytes; thread = (slab, row): one 32-byte row
-      const int c8 = tid >> 6, r = (tid >> 1) & 31, half = tid & 1;
-      const int t = t0 + r;
-      float4 v = make_float4(0, 0, 0, 0);
-      if (t < Tv) v = *reinterpret_cast<const float4*>(x + ((size_t)(d0 / 8 + c8) * Tr + r0 + t) * 8 + half * 4);
-      *reinterpret_cast<float4*>(&sx[(c8 * kKmTileT + r) * 8 + half * 4]) = v;
-      if (feat_out && t < T) *reinterpret_cast<float4*>(feat_out + ((size_t)b * T + t) * D + d0 + c8 * 8 + half * 4) = v;
-      // centroid chunk: K rows x 32 channels -> [quad][j][4]
-      for (int i = tid; i < kKmMaxK * 8; i += 256) {
-        const int j = i >> 3, q = i & 7;
-        float4 c = make_float4(0, 0, 0, 0);
-        if (j < K) c = __ldg(reinterpret_cast<const float4*>(cent + (size_t)j * D + d0 + q * 4));
-        *reinterpret_cast<float4*>(&sc[(q * kKmMaxK + j) * 4]) = c;
-      }
-    }
-    __syncthreads();
-    float acc[2][8];
-#pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[f][i] = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {       // channel quad of the chunk: slab q / 2, half q & 1
-      const float4 x0 = *reinterpret_cast<const float4*>(&sx[((q >> 1) * kKmTileT + 2 * fg) * 8 + (q & 1) * 4]);
-      const float4 x1 = *reinterpret_cast<const float4*>(&sx[((q >> 1) * kKmTileT + 2 * fg + 1) * 8 + (q & 1) * 4]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 c = *reinterpret_cast<const float4*>(&sc[(q * kKmMaxK + cg + 16 * i) * 4]);
-        float u;
-        u = x0.x - c.x; acc[0][i] = fmaf(u, u, acc[0][i]);
-        u = x0.y - c.y; acc[0][i] = fmaf(u, u, acc[0][i]);
-        u = x0.z - c.z; acc[0][i] = fmaf(u, u, acc[0][i]);
-        u = x0.w - c.w; acc[0][i] = fmaf(u, u, acc[0][i]);
-        u = x1.x - c.x; acc[1][i] = fmaf(u, u, acc[1][i]);
-        u = x1.y - c.y; acc[1][i] = fmaf(u, u, acc[1][i]);
-        u = x1.z - c.z; acc[1][i] = fmaf(u, u, acc[1][i]);
-        u = x1.w - c.w; acc[1][i] = fmaf(u, u, acc[1][i]);
-      }
-    }
-#pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tot[f][i] += acc[f][i];
+  if (t >= Tv) {
+    units[(size_t)b * T + t] = -1;
+    return;
   }
+  const size_t row = (size_t)row_off[b] + t;
+  float best = INFINITY;
+  int besti = 0;
+#pragma unroll 4
+  for (int g8 = 0; g8 < kKmMaxK / 8; ++g8) {
+    float4 a, c;
+    ldg8(dist + ((size_t)g8 * Tr + row) * 8, a, c);
+    const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-  for (int f = 0; f < 2; ++f) {
-    float best = INFINITY;
-    int besti = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {       // ascending index inside the thread: strict '<' keeps the lowest on ties
-      const int j = cg + 16 * i;
-      if (j < K && tot[f][i] < best) {
-        best = tot[f][i];
-        besti = j;
+    for (int i = 0; i < 8; ++i)
+      if (v[i] < best) {   // ascending index, strict '<': the lowest index wins ties
+        best = v[i];
+        besti = g8 * 8 + i;
       }
-    }
-#pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) {  // across the 16 centroid lanes (one half-warp)
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-      if (ob < best || (ob == best && oi < besti)) {
-        best = ob;
-        besti = oi;
-      }
-    }
-    const int t = t0 + 2 * fg + f;
-    if (cg == 0 && t < T) units[(size_t)b * T + t] = t < Tv ? besti : -1;
+  }
+  units[(size_t)b * T + t] = besti;
+}
+
+// dense features out: packed f32b [1][D8][Tr][8] -> (B, T, D) row-major, zeros past the valid length
+__global__ void __launch_bounds__(256) hub_features_out_kernel(const float* x, const int* lengths, const int* row_off, int D8,
+                                                               int T, int Tr, float* feat_out) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  const int Tv = lengths ? min(T, lengths[b]) : T;
+  const size_t row = (size_t)row_off[b] + t;
+  for (int i = threadIdx.x; i < D8 * 2; i += blockDim.x) {
+    const int c8 = i >> 1, half = i & 1;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (t < Tv) v = *reinterpret_cast<const float4*>(x + ((size_t)c8 * Tr + row) * 8 + half * 4);
+    *reinterpret_cast<float4*>(feat_out + ((size_t)b * T + t) * (D8 * 8) + c8 * 8 + half * 4) = v;
   }
 }
 
@@ -886,6 +842,9 @@ struct dissc_hubert {
   float *proj_b = nullptr, *pos_b = nullptr, *eln_w = nullptr, *eln_b = nullptr;
   std::vector<HubLayer> layers;
   float* cent = nullptr;
+  TcLayer km;               // the k-means codebook as a GEMM layer (K <= 128): W = -2 C, bias = |c|^2
+  float* km_b = nullptr;
+  bool km_gemm = false;
 };
 
 namespace dissc {
@@ -1174,6 +1133,23 @@ int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const
     if ((rc = hub_vec(g, wm, p + "final_layer_norm.bias", D, &Ly.ln2_b))) return fail(rc);
   }
   if ((rc = hub_vec(g, wm, "kmeans.cluster_centers", c.n_clusters * D, &g->cent))) return fail(rc);
+  if (c.n_clusters <= kKmMaxK && tc_plan(D, kKmMaxK, 1, 1, 0, &g->km, kHubHalo)) {
+    const float* cd = wm.get("kmeans.cluster_centers")->data;
+    const int K = c.n_clusters;
+    g->km.Cout = kKmMaxK;
+    auto packed = pack_weights_tc(g->km, [=](int n, int ci, int) { return n < K ? -2.f * cd[(size_t)n * D + ci] : 0.f; },
+                                  &g->km.inv_scale);
+    if ((rc = hub_upload_h(g, packed, &g->km.w))) return fail(rc);
+    std::vector<float> nb(kKmMaxK, FLT_MAX);   // padded columns never win
+    for (int n = 0; n < K; ++n) {
+      double acc = 0.0;
+      for (int i = 0; i < D; ++i) acc += (double)cd[(size_t)n * D + i] * (double)cd[(size_t)n * D + i];
+      nb[n] = (float)acc;
+    }
+    if ((rc = hub_upload_f(g, nb.data(), nb.size(), &g->km_b))) return fail(rc);
+    g->km.cluster2 = 1;
+    g->km_gemm = true;
+  }
   // the encoder's streamed-weight GEMMs stream 57 B/clk/SM of weights (the stride-2 frame form also loads the taps it
   // skips): 2-CTA clusters with one multicast weight stream are worth 1.6 % here (neutral in the vocoder, where they stay off)
   for (int l = 0; l < 6; ++l) g->conv[l].cluster2 = 1;
@@ -1352,9 +1328,17 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     HUB_TRY(packed_ln(bf.Y, Ly.ln2_w, Ly.ln2_b));
   }
   {
-    if (c.n_clusters <= kKmMaxK && D % kKmChunk == 0) {
-      hub_kmeans_tiled_kernel<<<B * ((T + kKmTileT - 1) / kKmTileT), 256, 0, st>>>(
-          bf.H, g->cent, lenT, row_off, B, D / 8, T, pk.Rr, c.n_clusters, reinterpret_cast<long long*>(units), features);
+    if (g->km_gemm) {
+      // distances (up to the per-row constant |x|^2) by one more GEMM on the layer-6 planes, into the idle QKV buffer
+      TcParams p = pbase();
+      p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = g->km_b; p.out_f32b = bf.QKV;
+      HUB_TRY(launch_conv_tc(p, g->km, pk.R, st));
+      hub_kmeans_argmin_kernel<<<B * ((T + 127) / 128), 128, 0, st>>>(bf.QKV, lenT, row_off, T, pk.Rr,
+                                                                       reinterpret_cast<long long*>(units));
+      if (features) {
+        DISSC_CUDA(cudaGetLastError());
+        hub_features_out_kernel<<<dim3(T, B), 192, 0, st>>>(bf.H, lenT, row_off, D / 8, T, pk.Rr, features);
+      }
     } else {
       const long long threads = (((long long)B * T + kKmFrames - 1) / kKmFrames) * 32;
       hub_kmeans_f32b_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(
