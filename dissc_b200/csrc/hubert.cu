@@ -529,15 +529,21 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
   //      loads (8 consecutive keys of one 8-dim slab: 128 contiguous bytes, lanes = consecutive key groups), 32 byte
   //      permutes, eight 16-byte shared stores (one per dim: its 8 keys).  The key-group stride of the V^T tile is padded
   //      to 2048 + 16 bytes so the 8 lanes of a store phase hit 8 different 16-byte bank groups.
-  for (int item = tid; item < (NK / 8) * 8; item += kAttnTcThreads) {
+  //      Warp 0 issues the TMA loads and the MMAs, so the items go to the other warps (the row-max pass below starts with a
+  //      CTA barrier: a late warp 0 would hold everybody up), and a thread has the loads of BOTH planes in flight before it
+  //      permutes the first -- L2 latency is what this phase costs.
+  for (int item = tid - 32; item >= 0 && item < (NK / 8) * 8; item += kAttnTcThreads - 32) {
     const int c8 = item / (NK / 8), kg = item - c8 * (NK / 8);
+    uint4 a[2][8];
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
       const __half* src = (pl ? q_lo : q_hi) + base_v + c8 * slab + (size_t)kg * 64;
-      uint4 a[8];
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk)
-        a[kk] = (kg * 8 + kk < Tv) ? *reinterpret_cast<const uint4*>(src + kk * 8) : make_uint4(0, 0, 0, 0);
+        a[pl][kk] = (kg * 8 + kk < Tv) ? *reinterpret_cast<const uint4*>(src + kk * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
       unsigned char* dst = sV + (size_t)kg * kVtStride + pl * 1024 + (size_t)(c8 * 8) * 16;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {       // dim n of the slab: its 8 keys, two per word
@@ -545,9 +551,9 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1) hub_attention_tc_kernel(con
         uint32_t o[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const uint32_t lo_w = (n >> 1) == 0 ? a[2 * w].x : (n >> 1) == 1 ? a[2 * w].y : (n >> 1) == 2 ? a[2 * w].z : a[2 * w].w;
-          const uint32_t hi_w = (n >> 1) == 0 ? a[2 * w + 1].x : (n >> 1) == 1 ? a[2 * w + 1].y : (n >> 1) == 2 ? a[2 * w + 1].z
-                                                                                                                : a[2 * w + 1].w;
+          const uint4 &e = a[pl][2 * w], &d = a[pl][2 * w + 1];
+          const uint32_t lo_w = (n >> 1) == 0 ? e.x : (n >> 1) == 1 ? e.y : (n >> 1) == 2 ? e.z : e.w;
+          const uint32_t hi_w = (n >> 1) == 0 ? d.x : (n >> 1) == 1 ? d.y : (n >> 1) == 2 ? d.z : d.w;
           o[w] = __byte_perm(lo_w, hi_w, sel);
         }
         *reinterpret_cast<uint4*>(dst + n * 16) = make_uint4(o[0], o[1], o[2], o[3]);
