@@ -61,16 +61,22 @@ def test_features_and_units_varlen_batch(cuda_device, setup):
 
 def _unit_checks(units, dense_gpu, feat64, cent, tag):
     """units: what the GPU assigned; dense_gpu: ITS OWN layer-6 features; feat64: the fp64 oracle's features.
-    (1) the quantiser is exact on the features it was given: units == fp64 argmin over dense_gpu wherever that argmin is
-        not a tie at fp32 resolution (relative margin > 1e-6);
+    (1) the quantiser is exact on the features it was given, up to the rounding of the form it evaluates: the assignment
+        computes |c|^2 - 2 x.c (the fairseq / sklearn form) as a split-fp16 GEMM with fp32 accumulation, so the fp64
+        distance of the chosen centroid may exceed the fp64 minimum by at most 1e-6 of the distance plus 2e-6 of
+        |x|^2 + max|c|^2 -- i.e. it IS the fp64 argmin except between centroids that tie at fp32 resolution;
     (2) against the oracle's units: a frame may differ only if the feature noise can provably flip it, i.e. the GPU's
         choice is within 2 * (|x - c_a| + |x - c_b|) * |delta| + |delta|^2 of the oracle's minimum distance, with delta
         the measured feature difference of that frame."""
     c64 = cent.double()
     d_own = ho.kmeans_distances(dense_gpu.double(), c64)
-    top2 = d_own.topk(2, dim=-1, largest=False).values
-    sure = (top2[:, 1] - top2[:, 0]) > 1e-6 * top2[:, 1]
-    assert torch.equal(units[sure], d_own.argmin(-1)[sure]), f"{tag}: k-means assign is not the exact argmin of its input"
+    best = d_own.min(-1).values
+    chosen = d_own.gather(1, units.view(-1, 1)).view(-1)
+    scale = dense_gpu.double().pow(2).sum(-1) + c64.pow(2).sum(-1).max()
+    excess = chosen - best
+    assert torch.all(excess <= 1e-6 * best + 2e-6 * scale), \
+        f"{tag}: k-means assign is not the argmin of its input (excess {excess.max():.3e}, scale {scale.max():.3e})"
+    assert (units == d_own.argmin(-1)).double().mean() > 0.9, f"{tag}: too many fp32-resolution ties for a meaningful check"
     d_ref = ho.kmeans_distances(feat64, c64)
     want = d_ref.argmin(-1)
     diff = units != want
@@ -188,6 +194,27 @@ def test_call_surface_matches_data_encode(cuda_device, setup):
     wave[0], wave[1, :lens[1]] = waves[0], waves[1]
     u, nf, _ = enc.encode_batch(wave.to(cuda_device), torch.tensor([lens[0], lens[1]], dtype=torch.int32))
     assert torch.equal(u[1, :T], out["units"])
+
+
+def test_encoder_kmeans_gemm_and_large_codebook(cuda_device, setup):
+    """The encoder's two assignment paths: K <= 128 (one more GEMM + row argmin) and K > 128 (CUDA-core kernel)."""
+    from dissc_b200.hubert import SpeechEncoder
+    sd, lens, waves, feats, cent = setup
+    g = torch.Generator().manual_seed(11)
+    wave = waves[0].view(1, -1).to(cuda_device)
+    # duplicate centroid: identical columns give identical distances, the lower index must win
+    dup = cent.clone()
+    dup[37] = dup[5]
+    u, _, dense = SpeechEncoder.from_state_dict(sd, dup).to(cuda_device).encode_batch(wave)
+    assert not bool((u == 37).any())
+    _unit_checks(u[0].cpu(), dense[0].cpu(), feats[0].double(), dup, "K=100 with a duplicate")
+    # 200 centroids: beyond the 128 GEMM columns
+    allf = torch.cat(feats, 0)
+    big = torch.cat([cent, allf[torch.randperm(allf.shape[0], generator=g)[:100]] + 0.02 * torch.randn(100, 768, generator=g)])
+    u2, _, dense2 = SpeechEncoder.from_state_dict(sd, big).to(cuda_device).encode_batch(wave)
+    same, n = _unit_checks(u2[0].cpu(), dense2[0].cpu(), feats[0].double(), big, "K=200")
+    assert same / n > 0.98 and bool((u2 >= 128).any())
+    assert torch.equal(dense.cpu(), dense2.cpu())
 
 
 def test_kmeans_assign_exact(cuda_device):
