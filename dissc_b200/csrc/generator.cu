@@ -210,7 +210,7 @@ extern int g_hub_attn_tc;        // hubert.cu: tensor-core attention (key 4)
 static int g_tc_cluster2 = -1;   // 2-CTA clusters with multicast weights (-1: env DISSC_TC_CLUSTER2 or the default 0)
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
-bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc) {
+bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc, int single_acc) {
   L->ok = false;
   if (Cin < 1 || taps < 1 || pad > halo || pad < 0) return false;
   if ((taps - 1) * dil - pad > halo) return false;  // right halo
@@ -246,8 +246,19 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
     g_tc_kb64 = e ? (atoi(e) != 0) : 1;
   }
   if (g_tc_kb64 && NC == 128 && L->Cin_pad % 64 == 0 && L->Cin_pad >= 128) L->KB = 64;
+  {
+    // 256-column single-accumulator chunks with one or two taps (the HuBERT GEMMs, which ask for them explicitly): a block of
+    // 32 channels is only 2 k-steps x 3 MMAs = 768 tensor cycles, and the per-block barrier round trips then cost ~10 % of
+    // the encoder (7.23 -> 6.93 ms per 32 clips with 64-channel blocks; DISSC_TC_KB64_256=0 restores 32)
+    static int kb64_256 = -1;
+    if (kb64_256 < 0) {
+      const char* e = getenv("DISSC_TC_KB64_256");
+      kb64_256 = e ? atoi(e) : 1;
+    }
+    if (kb64_256 && NC == 256 && single_acc == 1 && taps <= 2 && L->Cin_pad % 64 == 0 && L->Cin_pad >= 128) L->KB = 64;
+  }
   L->n_cb = L->Cin_pad / L->KB;
-  L->single_acc = (NC == 256) ? g_single_acc256 : 0;
+  L->single_acc = (NC == 256) ? (single_acc >= 0 ? single_acc : g_single_acc256) : 0;
   L->acc_cols = L->single_acc ? NC : 2 * NC;
   L->nbuf = (2 * L->acc_cols <= 512) ? 2 : 1;
   int cols = 32;

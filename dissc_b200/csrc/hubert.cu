@@ -902,12 +902,29 @@ static int hub_vec(dissc_hubert* g, const HubWeights& wm, const std::string& nam
   return hub_upload_f(g, t->data, n, out);
 }
 // Linear (Cout, Cin) [+ bias] as a k=1 tensor-core conv
+// 256-column chunks with ONE accumulator for the encoder's GEMMs (DISSC_HUB_NC256=0: 128-column chunks, main + cross).
+// These layers have one or two taps, so an activation tile is used for few MMAs and the operand stream from L2 -- not the
+// tensor pipe -- is what bounds them: 148 SMs sustain ~35 B/clk each, a 128 x 128 split-fp16 tile needs 64 at full MMA rate
+// (with the 2-CTA multicast weight stream), a 128 x 256 tile 43.
+static int hub_nc256(int ncols) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DISSC_HUB_NC256");
+    on = e ? (atoi(e) != 0) : 1;
+  }
+  return (on && ncols % 256 == 0) ? 256 : 0;
+}
+static bool hub_plan(int Cin, int ncols, int taps, TcLayer* L) {
+  const int nc = hub_nc256(ncols);
+  return tc_plan(Cin, ncols, taps, 1, 0, L, kHubHalo, nc, nc ? 1 : -1);
+}
+
 static int hub_linear(dissc_hubert* g, const HubWeights& wm, const std::string& name, int Cin, int Cout, TcLayer* L,
                       float** bias) {
   const dissc_tensor* w = wm.get(name + ".weight");
   DISSC_CHECK(w && w->numel == (int64_t)Cin * Cout, DISSC_EMISSING, "missing tensor %s.weight (%d,%d)", name.c_str(), Cout,
               Cin);
-  DISSC_CHECK(tc_plan(Cin, Cout, 1, 1, 0, L, kHubHalo), DISSC_EUNSUPPORTED, "%s: no tcgen05 plan for %d->%d", name.c_str(),
+  DISSC_CHECK(hub_plan(Cin, Cout, 1, L), DISSC_EUNSUPPORTED, "%s: no tcgen05 plan for %d->%d", name.c_str(),
               Cin, Cout);
   L->Cout = Cout;
   const float* wd = w->data;
@@ -1080,7 +1097,7 @@ int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const
     if (!w || w->numel != (int64_t)C * C * k) return fail(set_err(DISSC_EMISSING, "missing %s%d.0.weight (%d,%d,%d)", fe.c_str(), l, C, C, k));
     TcLayer* L = &g->conv[l - 1];
     const int taps = (k + 1) / 2;
-    if (!tc_plan(2 * C, C, taps, 1, 0, L, kHubHalo)) return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for extractor conv %d", l));
+    if (!hub_plan(2 * C, C, taps, L)) return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for extractor conv %d", l));
     L->Cout = C;
     if (k & 1) {
       // odd kernel: the last tap of the odd phase (jj = k) does not exist -> the second half of the channel blocks has
@@ -1132,7 +1149,7 @@ int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const
     if (!qw || !kw || !vw || !qb || !kb || !vb || qw->numel != (int64_t)D * D || kw->numel != qw->numel ||
         vw->numel != qw->numel || qb->numel != D || kb->numel != D || vb->numel != D)
       return fail(set_err(DISSC_EMISSING, "missing %sself_attn.{q,k,v}_proj.{weight,bias}", p.c_str()));
-    if (!tc_plan(D, 3 * D, 1, 1, 0, &Ly.qkv, kHubHalo)) return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for QKV"));
+    if (!hub_plan(D, 3 * D, 1, &Ly.qkv)) return fail(set_err(DISSC_EUNSUPPORTED, "no tcgen05 plan for QKV"));
     Ly.qkv.Cout = 3 * D;
     const float scaling = 0.125f;  // head_dim 64 ** -0.5 (fairseq MultiheadAttention.scaling)
     const float *qd = qw->data, *kd = kw->data, *vd = vw->data;
@@ -1170,14 +1187,18 @@ int dissc_hubert_create(dissc_hubert_t** out, const dissc_hubert_cfg* cfg, const
       nb[n] = (float)acc;
     }
     if ((rc = hub_upload_f(g, nb.data(), nb.size(), &g->km_b))) return fail(rc);
-    g->km.cluster2 = 1;
     g->km_gemm = true;
   }
   // the encoder's streamed-weight GEMMs stream 57 B/clk/SM of weights (the stride-2 frame form also loads the taps it
   // skips): 2-CTA clusters with one multicast weight stream are worth 1.6 % here (neutral in the vocoder, where they stay off)
-  for (int l = 0; l < 6; ++l) g->conv[l].cluster2 = 1;
-  g->proj.cluster2 = 1;
-  for (HubLayer& Ly : g->layers) Ly.qkv.cluster2 = Ly.out.cluster2 = Ly.fc1.cluster2 = Ly.fc2.cluster2 = 1;
+  {
+    const char* e = getenv("DISSC_HUB_CLUSTER2");   // A/B switch
+    const int cl = e ? (atoi(e) != 0) : 1;
+    for (int l = 0; l < 6; ++l) g->conv[l].cluster2 = cl;
+    g->proj.cluster2 = cl;
+    for (HubLayer& Ly : g->layers) Ly.qkv.cluster2 = Ly.out.cluster2 = Ly.fc1.cluster2 = Ly.fc2.cluster2 = cl;
+    if (g->km_gemm) g->km.cluster2 = cl;
+  }
   *out = g;
   return DISSC_OK;
 }

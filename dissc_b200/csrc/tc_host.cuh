@@ -30,7 +30,8 @@ constexpr size_t kSmemPerSm = 227 * 1024;
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows, left
 // padding `pad` rows; the plane buffers carry `halo` zero rows either side.
-bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc = 0);
+// force_nc: chunk width (0 = by the column count); single_acc: -1 = the process default (NC = 256 only)
+bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc = 0, int single_acc = -1);
 bool tc_plan_conv(int Cin, int Cout, int k, int dil, TcLayer* L);
 // p carries the tensors, B, T (output rows), Tr, Tp, Tp_in, lengths and the epilogue switches; `rows` is the number of
 // GEMM rows per utterance (output time steps for a conv, input frames for a transposed conv).
