@@ -1222,6 +1222,7 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
   DISSC_CHECK(B <= 65535, DISSC_EINVAL, "B=%d exceeds the grid limit 65535", B);
   const HubShapes s = hub_shapes(N);
   DISSC_CHECK(s.T[6] > 0, DISSC_EINVAL, "clips of %d samples are shorter than the 400-sample receptive field", N);
+  DISSC_CHECK((long long)B * s.T[6] < (1ll << 30), DISSC_EINVAL, "%d clips x %d frames exceed the packed row space", B, s.T[6]);
   size_t need = 0;
   dissc_hubert_workspace_bytes(g, B, N, &need);
   DISSC_CHECK(workspace && workspace_bytes >= need, DISSC_EINVAL, "workspace %zu bytes < required %zu", workspace_bytes, need);
