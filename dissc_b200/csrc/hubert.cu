@@ -47,6 +47,21 @@ __global__ void hub_lengths_kernel(const int* n_samples, int N, int B, int* lens
   }
 }
 
+// Debug aid (DISSC_HUB_RANGE_CHECK=1): counts the fp16 "hi" values of a plane tensor that sit at the format's limit
+// (|v| >= 65504: cvt.rn.satfinite clamped them) -- a real checkpoint with outlier activations beyond the fp16 range would
+// otherwise lose them silently.  Rows [halo, halo + rows) of every slab.
+__global__ void hub_range_check_kernel(const __half* hi, long long slabs, int Tp, int halo, int rows,
+                                       unsigned long long* count) {
+  const long long n = slabs * rows * 8;
+  unsigned long long local = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long slab = i / ((long long)rows * 8), rem = i - slab * rows * 8;
+    const unsigned short bits = reinterpret_cast<const unsigned short*>(hi)[(slab * Tp + halo) * 8 + rem];
+    local += (bits & 0x7fffu) >= 0x7bffu;
+  }
+  if (local) atomicAdd(count, local);
+}
+
 // row_off[b] = sum of the frame counts of clips 0 .. b-1 (row_off[B] = total): where clip b starts in the packed row
 // space of the transformer stack.  B <= a few thousand: one thread.
 __global__ void hub_row_offsets_kernel(const int* lens, int B, int T, int* row_off) {
@@ -982,6 +997,7 @@ static HubPacked hub_packed_rows(int B, int T) {
 struct HubBuffers {
   int* lens;
   int* row_off;   // B + 1: first packed row of every clip, then the total
+  unsigned long long* sat;   // DISSC_HUB_RANGE_CHECK: saturated fp16 activations seen in this forward
   double* gn_partial;   // [B][nchunk][65] wave moments
   float2* gn_ss;
   __half* dA[2];  // de-interleaved plane pairs (hi at [0], lo at hi + plane_elems)
@@ -1000,6 +1016,7 @@ static HubBuffers hub_layout(const dissc_hubert* g, int B, int N, void* ws) {
   const int nchunk = (std::max(s.T[0], 1) + kConv0Chunk - 1) / kConv0Chunk;
   b.lens = (int*)bp.take((size_t)7 * B * sizeof(int));
   b.row_off = (int*)bp.take((size_t)(B + 1) * sizeof(int));
+  b.sat = (unsigned long long*)bp.take(sizeof(unsigned long long));
   b.gn_partial = (double*)bp.take((size_t)B * nchunk * kWaveMoments * sizeof(double));
   b.gn_ss = (float2*)bp.take((size_t)B * C * sizeof(float2));
   auto plane_bytes = [&](int ch, int rows) { return (size_t)B * (ch / 8) * (ru(std::max(rows, 1), 128) + 2 * kHubHalo) * 16 + 4096; };
@@ -1233,6 +1250,17 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
   const dissc_hubert_cfg& c = g->cfg;
   const int C = c.conv_dim, D = c.embed_dim;
   HubBuffers bf = hub_layout(g, B, N, workspace);
+  // DISSC_HUB_RANGE_CHECK=1 (debug; synchronises): fail when an activation was clamped at the fp16 limit on its way into a
+  // plane tensor -- for first contact with a real checkpoint, whose outlier channels random look-alike weights do not have
+  static int range_check = -1;
+  if (range_check < 0) {
+    const char* e = getenv("DISSC_HUB_RANGE_CHECK");
+    range_check = e ? (atoi(e) != 0) : 0;
+  }
+  if (range_check) DISSC_CUDA(cudaMemsetAsync(bf.sat, 0, sizeof(unsigned long long), st));
+  auto check = [&](const __half* hi, long long slabs, int Tp_, int rows) {
+    if (range_check && rows > 0) hub_range_check_kernel<<<296, 256, 0, st>>>(hi, slabs, Tp_, kHubHalo, rows, bf.sat);
+  };
 
   hub_lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(n_samples, N, B, bf.lens);
   DISSC_CUDA(cudaGetLastError());
@@ -1255,6 +1283,7 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     hub_conv0_apply_kernel<<<dim3(nchunk_apply, B), 256, smem, st>>>(wave, g->w0, bf.gn_ss, bf.lens, N, C, Tp, kHubHalo,
                                                                      bf.dA[0], bf.dA[1]);
     DISSC_CUDA(cudaGetLastError());
+    check(bf.dA[0], (long long)B * 2 * C / 8, Tp, Tq);
   }
   // conv1..conv6 on the tensor cores
   __half* cur[2] = {bf.dA[0], bf.dA[1]};
@@ -1278,6 +1307,7 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
       p.out_f32b = bf.X6; p.pre_act = 2;  // GELU, then LayerNorm below
     }
     HUB_TRY(launch_conv_tc(p, g->conv[l - 1], Tout, st));
+    if (l < 6) check(nxt[0], (long long)B * 2 * C / 8, p.Tp, s.Tq[l]);
     std::swap(cur[0], nxt[0]);
     std::swap(cur[1], nxt[1]);
   }
@@ -1285,6 +1315,7 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
   // LayerNorm(512) -> planes; post_extract_proj -> x (f32b + planes)
   HUB_TRY(launch_zero_halos(bf.P6[0], bf.P6[1], B * C / 8, Tp, T, st, kHubHalo));
   HUB_TRY(hub_layernorm(bf.X6, g->ln0_w, g->ln0_b, lenT, B, C, T, Tr, Tp, nullptr, bf.P6[0], bf.P6[1], st));
+  check(bf.P6[0], (long long)B * C / 8, Tp, T);
   auto base = [&]() {
     TcParams p{};
     p.lengths = lenT; p.len_mul = 1; p.B = B; p.T = T; p.Tr = Tr; p.Tp = Tp; p.Tp_in = Tp; p.halo = kHubHalo;
@@ -1296,6 +1327,7 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     p.out_f32b = bf.X7; p.out_hi = bf.P7[0]; p.out_lo = bf.P7[1];
     HUB_TRY(launch_zero_halos(bf.P7[0], bf.P7[1], B * D / 8, Tp, T, st, kHubHalo));
     HUB_TRY(launch_conv_tc(p, g->proj, T, st));
+    check(bf.P7[0], (long long)B * D / 8, Tp, T);
   }
   {
     // x + GELU(pos_conv(x) + bias)   (fairseq TransformerEncoder.extract_features: x = x + x_conv)
@@ -1345,6 +1377,8 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
         p.out_f32b = bf.QKV;
       }
       HUB_TRY(launch_conv_tc(p, Ly.qkv, pk.R, st));
+      check(bf.PH[0], D / 8, pk.Rp, pk.R);
+      if (attn_tc) check(bf.PQ[0], 3 * D / 8, pk.Rp, pk.R);
     }
     if (attn_tc) {
       hub_attention_tc_kernel<<<dim3((T + 127) / 128, c.n_heads, B), kAttnTcThreads, kAttnTcSmem, st>>>(
@@ -1364,6 +1398,8 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
       TcParams p = pbase();
       p.a_hi = bf.PH[0]; p.a_lo = bf.PH[1]; p.bias = Ly.fc1_b; p.out_hi = bf.PF[0]; p.out_lo = bf.PF[1]; p.plane_act = 2;
       HUB_TRY(launch_conv_tc(p, Ly.fc1, pk.R, st));
+      check(bf.PH[0], D / 8, pk.Rp, pk.R);
+      check(bf.PF[0], c.ffn_dim / 8, pk.Rp, pk.R);
     }
     {
       TcParams p = pbase();
@@ -1392,6 +1428,14 @@ int dissc_hubert_forward(dissc_hubert_t* g, const float* wave, const int32_t* n_
     DISSC_CUDA(cudaGetLastError());
   }
   if (n_frames) DISSC_CUDA(cudaMemcpyAsync(n_frames, lenT, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (range_check) {
+    unsigned long long sat = 0;
+    DISSC_CUDA(cudaMemcpyAsync(&sat, bf.sat, sizeof(sat), cudaMemcpyDeviceToHost, st));
+    DISSC_CUDA(cudaStreamSynchronize(st));
+    DISSC_CHECK(sat == 0, DISSC_EUNSUPPORTED,
+                "%llu activations reached the fp16 limit (65504) in the split planes: this checkpoint needs activation scaling",
+                sat);
+  }
   return DISSC_OK;
 }
 

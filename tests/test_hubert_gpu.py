@@ -273,3 +273,38 @@ def test_encode_cli_end_to_end(cuda_device, setup, tmp_path):
         top2 = d.topk(2, dim=-1, largest=False).values
         sure = (top2[:, 1] - top2[:, 0]) / top2[:, 1].clamp(min=1e-12) > 1e-3
         assert torch.equal(torch.tensor(r["units"])[sure], d.argmin(-1)[sure])
+
+
+_RANGE_CHECK_SCRIPT = r"""
+import sys, torch, torchaudio
+from oracle import hubert_oracle as ho
+from dissc_b200.hubert import SpeechEncoder
+torch.manual_seed(0)
+sd = ho.from_torchaudio(torchaudio.models.hubert_base().eval(), 6)
+cent = torch.randn(100, 768)
+wave = 0.1 * torch.randn(2, 8000, device="cuda")
+SpeechEncoder.from_state_dict(sd, cent).to("cuda").encode_batch(wave)          # in range: passes
+hot = dict(sd)
+k = [n for n in hot if n.endswith("post_extract_proj.weight")][0]
+hot[k] = hot[k] * 1e6                                                           # projection output far beyond 65504
+try:
+    SpeechEncoder.from_state_dict(hot, cent).to("cuda").encode_batch(wave)
+except RuntimeError as e:
+    assert "fp16 limit" in str(e), e
+    print("RANGE_CHECK_OK")
+    sys.exit(0)
+sys.exit("saturated activations were not reported")
+"""
+
+
+def test_range_check_reports_saturated_activations(cuda_device):
+    """DISSC_HUB_RANGE_CHECK=1 (read once per process, hence the subprocess): a forward whose activations hit the fp16
+    limit on their way into the split planes fails loudly instead of quantising silently."""
+    import os
+    import subprocess
+    import sys
+    pytest.importorskip("torchaudio")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DISSC_HUB_RANGE_CHECK="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", _RANGE_CHECK_SCRIPT], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "RANGE_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
