@@ -349,6 +349,9 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
             int j0 = 0;
             for (int g = 0; g < p.SPC; ++g, j0 += p.JG) {
               const int nt = min(p.JG, p.k - j0);
+              // a stage made only of structurally zero taps (odd-kernel stride-2 frame form, second half of the channel
+              // blocks) is neither loaded nor waited for: the MMA thread skips it the same way
+              if (!p.resident && p.cb_split && cb >= p.cb_split && j0 >= p.k_hi) continue;
               const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
               if (!p.resident) mbar_wait(&w_empty[slot], wph ^ 1);
               const uint32_t wbytes = (uint32_t)nt * w_tap_bytes;
@@ -393,7 +396,8 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
           int j0 = 0;
           const int kc = (p.cb_split && cb >= p.cb_split) ? p.k_hi : p.k;   // taps with non-zero weights in this block
           for (int g = 0; g < p.SPC; ++g, j0 += p.JG) {
-            const int nt = min(p.JG, kc - j0);   // <= 0: the stage is only waited for and released
+            const int nt = min(p.JG, kc - j0);   // <= 0: resident weights: the stage is only waited for; streamed: skipped
+            if (!p.resident && nt <= 0) continue;   // (the weight producer did not load it either)
             const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
             if (!p.resident)
               mbar_wait(&w_full[slot], wph);
