@@ -97,6 +97,8 @@ struct TcParams {
   // different tiles of the same N chunk in lockstep; each loads half of every weight stage and multicasts it into both
   // CTAs' shared memory, which halves the L2 -> SM weight traffic (43 B/clk/SM without it, the chip's L2 limit).
   int cluster2;
+  int pair2;            // CTA pair issuing ONE 256-row tcgen05.mma.cta_group::2 per k-step: each CTA stages its own 128
+                        // activation rows and HALF the weight columns (see the kernel)
   int n_tiles;           // B * tiles_per_b
 };
 
@@ -134,6 +136,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // is free once BOTH CTAs' MMAs have read it)
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) forms: issued by the leader CTA for both ----
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
@@ -222,7 +242,9 @@ __device__ __forceinline__ void st_row8(float* p, const float v[8]) {
 __host__ __device__ constexpr int tc_pre_warps(int epw) { return epw == 8 ? 3 : 2; }
 __host__ __device__ constexpr int tc_threads(int epw) { return (tc_pre_warps(epw) + epw) * 32; }
 
-template <int NC, int EPW, int MODE>
+// PAIR: the CTA-pair form (p.pair2) is its own instantiation -- a kernel that merely CONTAINS cta_group::2 instructions can
+// only be launched as a cluster of two.
+template <int NC, int EPW, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) ? 3 : 2)) conv_tc_kernel(const TcParams p) {
   constexpr int PW = tc_pre_warps(EPW);   // warps in front of the epilogue warps
   constexpr int kTcThreads = tc_threads(EPW);
@@ -248,8 +270,17 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
   const uint32_t lbo_a = (uint32_t)R * 16;                        // bytes between 8-channel chunks of A
   const uint32_t a_plane_bytes = (uint32_t)(p.KB / 8) * lbo_a;    // one plane of one block
   const uint32_t a_bytes = 2 * a_plane_bytes;
-  constexpr uint32_t lbo_b = 2u * NC * 16;                        // [c8][hi|lo][NC][8]
-  const uint32_t w_tap_bytes = (uint32_t)(p.KB / 8) * lbo_b;
+  // CTA pair (tcgen05.mma.cta_group::2, M = 256): the pair walks (chunk, tile pair) items like the multicast clusters; each
+  // CTA stages the activation rows of ITS tile and the weight columns [rank * NC/2, rank * NC/2 + NC/2) of every stage --
+  // half the weight bytes per SM, which is what bounds the streamed-weight layers (shared-memory fill rate) -- and the
+  // leader (rank 0) issues every MMA for both.  The other CTA's MMA warp relays its "operands landed" barriers to the
+  // leader (a non-tensor cp.async.bulk cannot complete on another CTA's mbarrier: tried, the signal never arrives); slots
+  // are released in both CTAs by multicast commits.
+  constexpr bool pr2 = PAIR && (PW == 3);
+  const uint32_t wcols = pr2 ? (uint32_t)NC / 2 : (uint32_t)NC;   // weight columns staged by this CTA
+  const uint32_t lbo_b = 2u * wcols * 16;                         // [c8][hi|lo][wcols][8]
+  const uint32_t w_tap_bytes = (uint32_t)(p.KB / 8) * lbo_b;      // per CTA; the global stage holds both halves
+  const uint32_t w_tap_gbytes = pr2 ? 2 * w_tap_bytes : w_tap_bytes;
   const uint32_t w_slot_bytes = (uint32_t)p.JG * w_tap_bytes;
   unsigned char* sA = smem_raw;
   unsigned char* sW = sA + (size_t)p.NA * a_bytes;
@@ -266,8 +297,10 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // cluster mode: the pair (2i, 2i+1) walks "pair items" (chunk, tile pair) together; member r takes tile 2*pair + r.  An
   // odd tile count makes the last pair compute its last tile twice (identical stores) so both keep the same weight sequence.
-  const bool cl2 = (PW == 3) && p.cluster2;
+  const bool cl2 = (PW == 3) && (p.cluster2 || pr2);   // item mapping / cluster syncs shared by both pair modes
+  const bool mc2 = cl2 && !pr2;                            // multicast weight stream (two independent M = 128 MMAs)
   const uint32_t crank = cl2 ? cluster_ctarank() : 0;
+  const bool leader = !pr2 || crank == 0;
   const int it_first = cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int it_step = cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int it_count = cl2 ? ((p.n_tiles + 1) >> 1) * p.n_chunks : p.n_items;
@@ -278,17 +311,19 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
   };
 
   if (tid == 0) {
+    // pair mode, leader: "full" = own producer (+ bytes) and the partner's relay; "accumulator drained" = both epilogues
+    const uint32_t full_n = (pr2 && crank == 0) ? 2 : 1;
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&a_full[i], 1);
+      mbar_init(&a_full[i], full_n);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPW);
+      mbar_init(&acc_empty[i], (pr2 && crank == 0) ? 2 * EPW : EPW);
     }
     for (int i = 0; i < p.NS; ++i) {
-      mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], cl2 ? 2 : 1);
+      mbar_init(&w_full[i], full_n);
+      mbar_init(&w_empty[i], mc2 ? 2 : 1);
     }
     fence_mbar_init();
   }
@@ -301,9 +336,15 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
     s_bias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                 "r"(p.tmem_cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (pr2) {   // both CTAs of the pair, same warp, same shared-memory word
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                   "r"(p.tmem_cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                   "r"(p.tmem_cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -332,7 +373,7 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
         const __half* hi0 = p.a_hi + in0;
         const __half* lo0 = p.a_lo + in0;
         const unsigned char* wchunk = reinterpret_cast<const unsigned char*>(p.w) +
-                                      (size_t)chunk * p.n_cb * p.k * w_tap_bytes;
+                                      (size_t)chunk * p.n_cb * p.k * w_tap_gbytes;
         for (int cb = 0; cb < p.n_cb; ++cb) {
           if (do_a) {
             mbar_wait(&a_empty[abuf], aph ^ 1);
@@ -356,8 +397,13 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
               if (!p.resident) mbar_wait(&w_empty[slot], wph ^ 1);
               const uint32_t wbytes = (uint32_t)nt * w_tap_bytes;
               mbar_arrive_expect_tx(&w_full[slot], wbytes);
-              const unsigned char* wsrc = wchunk + ((size_t)cb * p.k + j0) * w_tap_bytes;
-              if (cl2) {
+              const unsigned char* wsrc = wchunk + ((size_t)cb * p.k + j0) * w_tap_gbytes;
+              if (pr2) {
+                // this CTA's column half of every tap of the stage ([tap][rank][...] in global memory)
+                for (int jj = 0; jj < nt; ++jj)
+                  tma_load_1d(sW + (size_t)slot * w_slot_bytes + (size_t)jj * w_tap_bytes,
+                              wsrc + (size_t)jj * w_tap_gbytes + crank * w_tap_bytes, w_tap_bytes, &w_full[slot]);
+              } else if (mc2) {
                 // this CTA's half of the stage, into BOTH CTAs' slot; the partner delivers the other half
                 const uint32_t half = wbytes >> 1;
                 tma_load_1d_multicast(sW + (size_t)slot * w_slot_bytes + crank * half, wsrc + crank * half, half,
@@ -372,12 +418,36 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
         first = false;
       }
     }
+  } else if (warp == 1 && !leader) {
+    // ===================== pair mode, second CTA: relay "operands landed" to the leader's barriers =====================
+    // Same walk as the MMA thread below; an arrival on the leader's a_full / w_full says this CTA's share of the block /
+    // stage is in ITS shared memory (the pair MMA reads both).
+    if (elect_one()) {
+      uint32_t abuf = 0, aph = 0, ws = 0, wph = 0;
+      const uint32_t a_full0 = mapa_u32(smem_u32(a_full), 0), w_full0 = mapa_u32(smem_u32(w_full), 0);
+      for (int item = it_first; item < it_count; item += it_step) {
+        for (int cb = 0; cb < p.n_cb; ++cb) {
+          mbar_wait(&a_full[abuf], aph);
+          mbar_arrive_cluster(a_full0 + abuf * 8);
+          if (++abuf == (uint32_t)p.NA) { abuf = 0; aph ^= 1; }
+          int j0 = 0;
+          const int kc = (p.cb_split && cb >= p.cb_split) ? p.k_hi : p.k;
+          for (int g = 0; g < p.SPC; ++g, j0 += p.JG) {
+            if (min(p.JG, kc - j0) <= 0) continue;
+            mbar_wait(&w_full[ws], wph);
+            mbar_arrive_cluster(w_full0 + ws * 8);
+            if (++ws == (uint32_t)p.NS) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (elect_one()) {
       // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
       constexpr uint32_t idesc_n = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * NC) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc_pair = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256
       const uint32_t sA0 = smem_u32(sA), sW0 = smem_u32(sW);
       const int KS = p.KB / 16;
       const uint32_t a_kstep = (2 * lbo_a) >> 4, b_kstep = (2 * lbo_b) >> 4;  // descriptor units (16 B)
@@ -385,13 +455,13 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
       uint32_t abuf = 0, aph = 0, ws = 0, wph = 0, ab = 0, accph = 0;
       bool first = true;
       for (int item = it_first; item < it_count; item += it_step) {
-        mbar_wait(&acc_empty[ab], accph ^ 1);
+        if (pr2) mbar_wait_cluster(&acc_empty[ab], accph ^ 1); else mbar_wait(&acc_empty[ab], accph ^ 1);
         tc_fence_after();
         const uint32_t d_main = tmem_base + ab * (uint32_t)p.acc_cols;
         const uint32_t d_cross = single_acc ? d_main : d_main + NC;
         uint32_t accum = 0;
         for (int cb = 0; cb < p.n_cb; ++cb) {
-          mbar_wait(&a_full[abuf], aph);
+          if (pr2) mbar_wait_cluster(&a_full[abuf], aph); else mbar_wait(&a_full[abuf], aph);
           const uint32_t a_desc0 = umma_desc_lo(sA0 + abuf * a_bytes, lbo_a);
           int j0 = 0;
           const int kc = (p.cb_split && cb >= p.cb_split) ? p.k_hi : p.k;   // taps with non-zero weights in this block
@@ -399,7 +469,9 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
             const int nt = min(p.JG, kc - j0);   // <= 0: resident weights: the stage is only waited for; streamed: skipped
             if (!p.resident && nt <= 0) continue;   // (the weight producer did not load it either)
             const uint32_t slot = p.resident ? (uint32_t)(cb * p.SPC + g) : ws;
-            if (!p.resident)
+            if (pr2)
+              mbar_wait_cluster(&w_full[slot], wph);
+            else if (!p.resident)
               mbar_wait(&w_full[slot], wph);
             else if (first)
               mbar_wait(&w_full[slot], 0);
@@ -409,7 +481,12 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
             for (int jj = 0; jj < nt; ++jj, a_desc += (uint32_t)p.dil, w_desc += (w_tap_bytes >> 4)) {
               uint32_t ad = a_desc, wd = w_desc;
               for (int ks = 0; ks < KS; ++ks, ad += a_kstep, wd += b_kstep) {
-                if constexpr (kTwoMma) {
+                if (pr2) {
+                  // three M = 256 MMAs; this CTA's weight columns sit at the same offsets in the partner's stage
+                  umma2_f16(d_main, umma_desc(ad), umma_desc(wd), idesc_pair, accum);
+                  umma2_f16(d_cross, umma_desc(ad + a_lo_off), umma_desc(wd), idesc_pair, single_acc ? 1u : accum);
+                  umma2_f16(d_cross, umma_desc(ad), umma_desc(wd + NC / 2), idesc_pair, 1);
+                } else if constexpr (kTwoMma) {
                   umma_f16(d_main, umma_desc(ad), umma_desc(wd), idesc_2n, accum);            // [main | cross]
                   umma_f16(d_cross, umma_desc(ad + a_lo_off), umma_desc(wd), idesc_n, 1);     // cross += lo*hi
                 } else {
@@ -421,17 +498,19 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
               }
             }
             if (!p.resident) {
-              if (cl2)
+              if (pr2)
+                umma2_commit_multicast(&w_empty[slot], (uint16_t)3);  // the pair MMA has read both CTAs' halves
+              else if (mc2)
                 umma_commit_multicast(&w_empty[slot], (uint16_t)3);   // frees the slot in both CTAs of the pair
               else
                 umma_commit(&w_empty[slot]);
             }
             if (++ws == (uint32_t)p.NS) { ws = 0; wph ^= 1; }
           }
-          umma_commit(&a_empty[abuf]);
+          if (pr2) umma2_commit_multicast(&a_empty[abuf], (uint16_t)3); else umma_commit(&a_empty[abuf]);
           if (++abuf == (uint32_t)p.NA) { abuf = 0; aph ^= 1; }
         }
-        umma_commit(&acc_full[ab]);
+        if (pr2) umma2_commit_multicast(&acc_full[ab], (uint16_t)3); else umma_commit(&acc_full[ab]);
         if (++ab == (uint32_t)p.nbuf) { ab = 0; accph ^= 1; }
         first = false;
       }
@@ -583,7 +662,12 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      if (lane == 0) {
+        if (pr2 && crank != 0)
+          mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[ab]), 0));   // the leader's MMA thread waits for both epilogues
+        else
+          mbar_arrive(&acc_empty[ab]);
+      }
       if (++ab == (uint32_t)p.nbuf) { ab = 0; accph ^= 1; }
     }
   }
@@ -592,7 +676,10 @@ __global__ void __launch_bounds__(tc_threads(EPW), (EPW == 8) ? 1 : ((NC <= 32) 
   __syncthreads();
   if (cl2) cluster_sync_all();   // neither CTA leaves while the other may still multicast into it / arrive on its barriers
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+    if (pr2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
   }
 }
 

@@ -210,8 +210,9 @@ extern int g_hub_attn_tc;        // hubert.cu: tensor-core attention (key 4)
 static int g_tc_cluster2 = -1;   // 2-CTA clusters with multicast weights (-1: env DISSC_TC_CLUSTER2 or the default 0)
 
 // Cin input channels, ncols GEMM columns (Cout, or u*Cout for a transposed conv), `taps` shifted by `dil` rows.
-bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc, int single_acc) {
+bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int halo, int force_nc, int single_acc, int pair2) {
   L->ok = false;
+  L->pair2 = 0;
   if (Cin < 1 || taps < 1 || pad > halo || pad < 0) return false;
   if ((taps - 1) * dil - pad > halo) return false;  // right halo
   if (g_tc_split256 < 0) {
@@ -266,7 +267,7 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
   L->tmem_cols = cols;
   const int R = 128 + (taps - 1) * dil;
   const size_t a_bytes = (size_t)4 * L->KB * R;
-  const size_t w_tap = (size_t)4 * L->KB * NC;
+  const size_t w_tap = (size_t)4 * L->KB * NC / (pair2 ? 2 : 1);   // bytes of one tap of a stage in ONE CTA's shared memory
   L->SPC = (int)std::max<size_t>(1, ((size_t)taps * w_tap + 32767) / 32768);
   L->JG = (taps + L->SPC - 1) / L->SPC;
   L->SPC = (taps + L->JG - 1) / L->JG;
@@ -277,7 +278,7 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
   for (int ctas = cap; ctas >= 1; --ctas) {
     const size_t budget = kSmemPerSm / ctas - 1536;  // static shared + alignment + per-CTA reservation
     auto misc = [&](int ns) { return (size_t)((L->n_chunks * NC + 1) & ~1) * 4 + (size_t)(12 + 2 * ns) * 8 + 128; };
-    if (L->n_chunks == 1 && total_slots <= kTcMaxStages) {
+    if (!pair2 && L->n_chunks == 1 && total_slots <= kTcMaxStages) {
       for (int na = 4; na >= 2; --na) {
         const size_t need = (size_t)na * a_bytes + (size_t)total_slots * slot + misc(total_slots);
         if (need <= budget) {
@@ -301,11 +302,13 @@ bool tc_plan(int Cin, int ncols, int taps, int dil, int pad, TcLayer* L, int hal
       const size_t fixed = (size_t)na * a_bytes + misc(8);
       if (budget <= fixed + 2 * slot) continue;
       const int ns = (int)std::min<size_t>(8, (budget - fixed) / slot);
-      if (na > 2 && ns < 4) continue;
+      if (na > 2 && ns < (pair2 ? 3 : 4)) continue;
       L->resident = 0; L->NA = na;
       L->NS = ns;
       L->smem = (size_t)na * a_bytes + (size_t)L->NS * slot + misc(L->NS);
       L->ctas_per_sm = ctas; L->ok = true;
+      L->pair2 = (pair2 && NC >= 128 && ctas == 1 && L->split_w) ? 1 : 0;
+      if (pair2 && !L->pair2) { L->ok = false; return false; }   // the caller asked for the pair layout: no silent fallback
       return true;
     }
   }
@@ -380,22 +383,37 @@ static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem,
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <int NC, int EPW, int MODE>
+template <int NC, int EPW, int MODE, bool PAIR = false>
 static int launch_conv_tc_inst(const TcParams& p, const TcLayer& L, int grid, cudaStream_t st) {
   static bool attr_set[kMaxDevices] = {};   // the attribute is per device: one flag per device ordinal
   const int dev_ = current_device_slot();
   if (!attr_set[dev_]) {
-    DISSC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NC, EPW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DISSC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NC, EPW, MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(kSmemPerSm - 1024)));
     attr_set[dev_] = true;
   }
-  DISSC_CUDA(launch_pdl(conv_tc_kernel<NC, EPW, MODE>, grid, tc_threads(EPW), L.smem, st, p, p.cluster2 ? 2 : 1));
+  const cudaError_t le = launch_pdl(conv_tc_kernel<NC, EPW, MODE, PAIR>, grid, tc_threads(EPW), L.smem, st, p,
+                                    (p.cluster2 || PAIR) ? 2 : 1);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    return set_err(DISSC_ECUDA, "conv_tc_kernel<%d,%d,%d> grid %d cluster %d pair %d smem %zu tiles %d chunks %d: %s", NC, EPW, MODE,
+                   grid, p.cluster2, p.pair2, L.smem, p.n_tiles, p.n_chunks, cudaGetErrorString(le));
+  }
   DISSC_CUDA(cudaGetLastError());
   return DISSC_OK;
 }
 
 template <int NC, int EPW>
 static int launch_conv_tc_mode(const TcParams& p, const TcLayer& L, int mode, int grid, cudaStream_t st) {
+  if constexpr (NC >= 128 && EPW == 8) {
+    if (p.pair2) {   // CTA-pair instantiations: plain convs and the generic epilogue
+      if (mode == kTcConv) return launch_conv_tc_inst<NC, EPW, kTcConv, true>(p, L, grid, st);
+      if (mode == kTcGeneric) return launch_conv_tc_inst<NC, EPW, kTcGeneric, true>(p, L, grid, st);
+      return set_err(DISSC_EUNSUPPORTED, "no CTA-pair kernel for transposed convs");
+    }
+  } else {
+    if (p.pair2) return set_err(DISSC_EINVAL, "CTA-pair plan on a %d-column chunk", NC);
+  }
   switch (mode) {
     case kTcConv: return launch_conv_tc_inst<NC, EPW, kTcConv>(p, L, grid, st);
     case kTcUp: return launch_conv_tc_inst<NC, EPW, kTcUp>(p, L, grid, st);
@@ -459,7 +477,13 @@ int launch_conv_tc(TcParams p, const TcLayer& L, int rows, cudaStream_t st) {
   }
   const bool epw8 = L.NC >= 128 || (L.NC == 64 && L.ctas_per_sm == 1 && g_tc_epw64 == 8 && mode != kTcGeneric);
   p.cluster2 = 0;
-  if ((L.cluster2 < 0 ? g_tc_cluster2 : L.cluster2) && epw8 && !L.resident && L.split_w && L.ctas_per_sm == 1 && p.n_tiles >= 2) {
+  p.pair2 = 0;
+  if (L.pair2) {
+    // weights are packed per column half: always the pair form (a lone tile is computed by both CTAs)
+    const int pair_items = ((p.n_tiles + 1) / 2) * L.n_chunks;
+    grid = std::max(2, std::min(2 * pair_items, num_sms()) & ~1);
+    p.pair2 = 1;
+  } else if ((L.cluster2 < 0 ? g_tc_cluster2 : L.cluster2) && epw8 && !L.resident && L.split_w && L.ctas_per_sm == 1 && p.n_tiles >= 2) {
     const int pair_items = ((p.n_tiles + 1) / 2) * L.n_chunks;
     grid = std::min(2 * pair_items, num_sms()) & ~1;
     p.cluster2 = grid >= 2 ? 1 : 0;

@@ -931,6 +931,12 @@ static int hub_nc256(int ncols) {
 }
 static bool hub_plan(int Cin, int ncols, int taps, TcLayer* L) {
   const int nc = hub_nc256(ncols);
+  static int pair = -1;   // DISSC_HUB_PAIR2=1: CTA pairs with 256-row cta_group::2 MMAs (conv_tc.cuh)
+  if (pair < 0) {
+    const char* e = getenv("DISSC_HUB_PAIR2");
+    pair = e ? (atoi(e) != 0) : 0;
+  }
+  if (nc && pair && tc_plan(Cin, ncols, taps, 1, 0, L, kHubHalo, nc, 1, 1)) return true;
   return tc_plan(Cin, ncols, taps, 1, 0, L, kHubHalo, nc, nc ? 1 : -1);
 }
 

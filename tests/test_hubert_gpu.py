@@ -308,3 +308,41 @@ def test_range_check_reports_saturated_activations(cuda_device):
     env = dict(os.environ, DISSC_HUB_RANGE_CHECK="1", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-c", _RANGE_CHECK_SCRIPT], env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "RANGE_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+_PAIR_SCRIPT = r"""
+import sys, torch, torchaudio
+from oracle import hubert_oracle as ho
+from dissc_b200.hubert import SpeechEncoder
+torch.manual_seed(0)
+sd = ho.from_torchaudio(torchaudio.models.hubert_base().eval(), 6)
+g = torch.Generator().manual_seed(5)
+lens = [12000, 7000, 9001]
+waves = [0.1 * torch.randn(n, generator=g) for n in lens]
+cent = torch.randn(100, 768, generator=g)
+wave = torch.zeros(len(lens), max(lens))
+for b, w in enumerate(waves):
+    wave[b, :len(w)] = w
+units, nf, dense = SpeechEncoder.from_state_dict(sd, cent).to("cuda").encode_batch(wave.cuda(), torch.tensor(lens, dtype=torch.int32))
+worst = 0.0
+for b, w in enumerate(waves):
+    f = ho.extract_features(sd, w.view(1, -1), 6)[0]
+    T = f.shape[0]
+    assert int(nf[b]) == T
+    worst = max(worst, (dense[b, :T].cpu() - f).abs().max().item())
+assert worst < 2e-4, worst
+print("PAIR_OK %.2e" % worst)
+"""
+
+
+def test_cta_pair_gemms_opt_in(cuda_device):
+    """DISSC_HUB_PAIR2=1: the encoder's GEMMs as CTA pairs issuing 256-row tcgen05.mma.cta_group::2 (conv_tc.cuh; opt-in,
+    measured 4 % slower than the single-CTA form): same features within the encoder's 2e-4 bound."""
+    import os
+    import subprocess
+    import sys
+    pytest.importorskip("torchaudio")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DISSC_HUB_PAIR2="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", _PAIR_SCRIPT], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PAIR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
